@@ -1,0 +1,148 @@
+/*
+ * sfh_b200.h — C ABI of the B200-native STN warp stage (libsfh_b200.so).
+ *
+ * The reference (darkAlert/sports-field-homography) is pure Python: the "FFI" this library
+ * replaces is the Python module boundary of the Reconstructor's warp stage.  Each entry point
+ * names the reference interface it stands in for (file:line under the reference tree).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching allocator in the
+ *     shipped host code); the library never allocates, frees or retains device memory;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *     nothing here synchronises;
+ *   - return value: 0 on success, a positive cudaError_t for CUDA failures, a negative
+ *     SFH_E_* code for argument errors.  No exceptions cross this boundary;
+ *   - theta is [B,3,3] row-major fp32 and maps OUTPUT-frame normalised coords to TEMPLATE
+ *     normalised coords (no inversion), exactly as kornia's HomographyWarper consumes it;
+ *   - xs[W] / ys[H] are the 1-D factors of kornia's create_meshgrid; NULL means "compute
+ *     (i/(n-1) - 0.5) * 2 with IEEE division in the kernel".
+ */
+#ifndef SFH_B200_H_
+#define SFH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFH_ABI_VERSION 1
+
+/* argument-error codes (negative) */
+#define SFH_E_BADARG   (-1)
+#define SFH_E_BADFMT   (-2)
+#define SFH_E_BADMODE  (-3)
+#define SFH_E_WS       (-4)
+
+/* interpolation mode: HomographyWarper(mode=...) — models/reconstructor.py:105,107 */
+#define SFH_MODE_BILINEAR 0
+#define SFH_MODE_NEAREST  1
+
+/* reconstruction criterion — train.py:113-116 (nn.MSELoss / nn.SmoothL1Loss, reduction='none') */
+#define SFH_LOSS_MSE      0
+#define SFH_LOSS_SMOOTHL1 1
+
+/* template storage formats */
+#define SFH_TMPL_F32 0  /* [Bt,C,Hc,Wc] fp32 as open_court_template returns it (utils/dataset.py:47-61) */
+#define SFH_TMPL_Q2  1  /* quad-packed palette indices, 2 bits/tap, uint8  [(Hc+1) x pitch] */
+#define SFH_TMPL_Q4  2  /* quad-packed palette indices, 4 bits/tap, uint16 [(Hc+1) x pitch] */
+
+/* Template descriptor.  For Q2/Q4, entry (j,i) holds the palette indices of the 2x2
+ * neighbourhood whose top-left texel is (y=j-1, x=i-1); texels outside the image are palette
+ * index 0 and palette[0] must be 0.0f (= padding_mode='zeros').  C must be 1 for Q2/Q4. */
+typedef struct sfh_template {
+    const void* data;        /* device pointer */
+    int32_t     fmt;         /* SFH_TMPL_* */
+    int32_t     channels;    /* C */
+    int32_t     height;      /* Hc */
+    int32_t     width;       /* Wc */
+    int32_t     pitch;       /* Q2/Q4: elements per packed row (>= Wc+1); F32: ignored */
+    int32_t     n_palette;   /* Q2/Q4: number of valid palette entries */
+    int64_t     batch_stride;/* F32: elements between consecutive samples, 0 = one shared template */
+    float       palette[16]; /* Q2/Q4: texel value of each palette index */
+} sfh_template;
+
+int sfh_abi_version(void);
+const char* sfh_build_info(void);
+const char* sfh_error_string(int code);
+
+/* Bytes of scratch the fused entry points need for a batch of B samples warped to HxW.
+ * The workspace must be zero-filled once when it is allocated; every call leaves it zeroed. */
+int64_t sfh_workspace_bytes(int B, int H, int W);
+
+/* Pack a class-index template (fp32 [Hc,Wc], every texel equal to one of palette[0..n)) into
+ * the Q2 (n<=4) or Q4 (n<=16) layout.  *err_flag (device int32, pre-zeroed) is set to 1 if a
+ * texel matches no palette entry.  Replaces nothing in the reference: it is the "stage the
+ * template once" step; source data is open_court_template's tensor (utils/dataset.py:47-61). */
+int sfh_template_pack(const float* tmpl, int Hc, int Wc, const float* palette_host, int n_palette,
+                      void* packed, int pitch, int fmt, int32_t* err_flag, void* stream);
+
+/* kornia HomographyWarper.forward(patch_src, src_homo_dst) — models/reconstructor.py:116
+ * (Reconstructor.warp, :109-118).  out: [B,C,H,W] fp32. */
+int sfh_warp_fwd(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
+                 int B, int H, int W, int mode, float* out, void* stream);
+
+/* autograd of the above w.r.t. theta (train.py:235 loss.backward() through grid_sample/bmm).
+ * grad_out [B,C,H,W] fp32 -> dtheta [B,3,3] fp32.  Bilinear only (nearest has zero gradient). */
+int sfh_warp_bwd(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
+                 const float* grad_out, int B, int H, int W, float* dtheta,
+                 void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Fused training tail, one pass over the pixels:
+ *   warp_mask = warp(theta)                               models/reconstructor.py:191
+ *   L_b = mean_{h,w} crit(warp_mask, gt/nc)               train.py:194-197, models/losses.py:35-38
+ *   J_b = dL_b/dtheta_b
+ * and, when court_poi != NULL, in the same launch:
+ *   poi = transform_poi(theta, court_poi)                 models/reconstructor.py:186,120-130
+ *   R_b = sum_n ||gt_poi-poi|| * nonzeros / num_nonzero   models/losses.py:10-11
+ *   K_b = dR_b/dtheta_b
+ * gt [B,H,W] int64 (utils/dataset.py:167).  warp_out (fp32 [B,H,W]) and the reprojection
+ * arguments are nullable.  Template must have C == 1. */
+int sfh_warp_loss_fwd_bwd(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
+                          const int64_t* gt, int nc, int kind, int B, int H, int W,
+                          float* warp_out, float* L_b, float* dLb_dtheta,
+                          const float* court_poi, int64_t court_poi_bstride, int N,
+                          const float* gt_poi, const float* nonzeros, const float* num_nonzero,
+                          float* poi_out, float* R_b, float* dRb_dtheta,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Reconstructor.predict tail — models/reconstructor.py:221-245:
+ *   warp_out = int32(warp(theta) * nc)            [B,H,W]
+ *   score_b  = mean CE(logits, int64(resize_nearest(warp*nc)))   logits [B,nc,h,w]  (nullable)
+ *   poi_out  = transform_poi(theta, court_poi)    (nullable) */
+int sfh_predict_tail(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
+                     int mode, int nc, const float* logits, int h, int w, int B, int H, int W,
+                     int32_t* warp_out, float* score,
+                     const float* court_poi, int64_t court_poi_bstride, int N, float* poi_out,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Reconstructor.transform_poi — models/reconstructor.py:120-130:
+ * poi = transform_points(inverse(theta), court_poi) [/2 + 0.5 if normalize].  fp64 inside. */
+int sfh_poi_fwd(const float* theta, const float* court_poi, int64_t court_poi_bstride,
+                int B, int N, int normalize, float* poi_out, void* stream);
+
+/* autograd of sfh_poi_fwd: grad_poi [B,N,2] -> dtheta [B,3,3]. */
+int sfh_poi_bwd(const float* theta, const float* court_poi, int64_t court_poi_bstride,
+                const float* grad_poi, int B, int N, int normalize, float* dtheta, void* stream);
+
+/* kornia.geometry.linalg.transform_points(trans_01, points_1) — models/reconstructor.py:124.
+ * trans [Bt,3,3] with Bt in {1,B}; points [B,N,2] -> out [B,N,2] (fp32 op order of the
+ * reference: bmm chain, 1/z where |z|>1e-8). */
+int sfh_transform_points_fwd(const float* trans, int Bt, const float* points, int B, int N,
+                             float* out, void* stream);
+
+/* autograd of the above: grad_out [B,N,2] -> dtrans [Bt,3,3] (nullable), dpoints [B,N,2] (nullable) */
+int sfh_transform_points_bwd(const float* trans, int Bt, const float* points, const float* grad_out,
+                             int B, int N, float* dtrans, float* dpoints, void* stream);
+
+/* models/losses.py:6-18 reprojection_loss per-sample part and its gradient w.r.t. `inputs`:
+ * R_b = sum_n sqrt(sum_xy (targets-inputs)^2) * nonzeros / num_nonzero;
+ * dinputs (nullable) = grad_Rb[b] * dR_b/dinputs. */
+int sfh_reproj_loss(const float* inputs, const float* targets, const float* nonzeros,
+                    const float* num_nonzero, int B, int N, float* R_b,
+                    const float* grad_Rb, float* dinputs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFH_B200_H_ */

@@ -1,0 +1,12 @@
+"""Import shim: ``import sfh_b200`` loads the package that lives in the directory
+``sports-field-homography_b200/`` (a hyphen cannot appear in a Python module name)."""
+import importlib.util as _u
+import os as _os
+import sys as _sys
+
+_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "sports-field-homography_b200")
+_spec = _u.spec_from_file_location("sfh_b200", _os.path.join(_dir, "__init__.py"),
+                                   submodule_search_locations=[_dir])
+_mod = _u.module_from_spec(_spec)
+_sys.modules["sfh_b200"] = _mod
+_spec.loader.exec_module(_mod)

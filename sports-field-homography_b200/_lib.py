@@ -1,0 +1,105 @@
+"""ctypes binding of libsfh_b200.so (C ABI declared in include/sfh_b200.h).
+
+There is no CPU fallback: if the library is missing or a tensor is not on a CUDA device the
+call fails loudly.  The library itself never sees a torch type — only raw device pointers,
+sizes and the current stream handle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libsfh_b200.so")
+CSRC = [os.path.join(_HERE, "csrc", f) for f in ("sfh_warp.cu", "sfh_poi.cu")]
+HDRS = [os.path.join(_HERE, "csrc", f) for f in ("sfh_device.cuh", "sfh_poi.cuh")] + \
+       [os.path.join(_ROOT, "include", "sfh_b200.h")]
+
+MODE = {"bilinear": 0, "nearest": 1}
+LOSS = {"MSE": 0, "SmoothL1": 1}
+TMPL_F32, TMPL_Q2, TMPL_Q4 = 0, 1, 2
+
+
+class SfhTemplate(C.Structure):
+    """struct sfh_template (include/sfh_b200.h)."""
+    _fields_ = [("data", C.c_void_p), ("fmt", C.c_int32), ("channels", C.c_int32),
+                ("height", C.c_int32), ("width", C.c_int32), ("pitch", C.c_int32),
+                ("n_palette", C.c_int32), ("batch_stride", C.c_int64), ("palette", C.c_float * 16)]
+
+
+_P = C.c_void_p
+_I = C.c_int
+_L = C.c_int64
+_T = C.POINTER(SfhTemplate)
+
+# name -> (restype, argtypes); must list every symbol include/sfh_b200.h declares
+SIGNATURES = {
+    "sfh_abi_version": (_I, []),
+    "sfh_build_info": (C.c_char_p, []),
+    "sfh_error_string": (C.c_char_p, [_I]),
+    "sfh_workspace_bytes": (_L, [_I, _I, _I]),
+    "sfh_template_pack": (_I, [_P, _I, _I, C.POINTER(C.c_float), _I, _P, _I, _I, _P, _P]),
+    "sfh_warp_fwd": (_I, [_P, _T, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "sfh_warp_bwd": (_I, [_P, _T, _P, _P, _P, _I, _I, _I, _P, _P, _L, _P]),
+    "sfh_warp_loss_fwd_bwd": (_I, [_P, _T, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P,
+                                   _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    "sfh_predict_tail": (_I, [_P, _T, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P,
+                              _P, _L, _I, _P, _P, _L, _P]),
+    "sfh_poi_fwd": (_I, [_P, _P, _L, _I, _I, _I, _P, _P]),
+    "sfh_poi_bwd": (_I, [_P, _P, _L, _P, _I, _I, _I, _P, _P]),
+    "sfh_transform_points_fwd": (_I, [_P, _I, _P, _I, _I, _P, _P]),
+    "sfh_transform_points_bwd": (_I, [_P, _I, _P, _P, _I, _I, _P, _P, _P]),
+    "sfh_reproj_loss": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+}
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "--compiler-options", "-fPIC", "-shared"]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = CSRC + HDRS
+    if not force and os.path.exists(LIB_PATH) and \
+            os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH] + CSRC
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("nvcc failed building libsfh_b200.so")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`."
+                " sfh_b200 has no CPU or eager fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)          # AttributeError => header/ABI mismatch, fail loudly
+            fn.restype, fn.argtypes = res, args
+        if l.sfh_abi_version() != 1:
+            raise RuntimeError("libsfh_b200.so ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().sfh_error_string(rc).decode()
+        if rc < 0:
+            raise ValueError(f"{what}: {msg}")
+        raise RuntimeError(f"{what}: CUDA error {rc}: {msg}")

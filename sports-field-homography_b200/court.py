@@ -1,0 +1,139 @@
+"""Court template / point-of-interest providers and the packed template format.
+
+Mirrors ``open_court_template`` / ``open_court_poi`` of the reference
+(utils/dataset.py:47-61, 63-96; numpy twins utils/court.py:56-99): same arguments, same
+returned tensors, so a caller can swap the import.  ``CourtTemplate`` adds the "stage the
+template once" step of the B200 path: a class-index template is converted, on the GPU, into the
+quad-packed palette format the kernels sample with one load per output pixel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+def open_court_template(path, num_classes, size=None, batch_size=1):
+    """utils/dataset.py:47-61 — PIL open, NEAREST resize to (W,H), /num_classes, [B,1,H,W] fp32."""
+    from PIL import Image
+    template = Image.open(path)
+    if size is not None:
+        template = template.resize(size, resample=Image.NEAREST)
+    template = np.array(template) / float(num_classes)
+    template_tensor = torch.from_numpy(template).type(torch.FloatTensor)
+    while template_tensor.ndim < 4:
+        template_tensor = template_tensor.unsqueeze(0)
+    return template_tensor.repeat(batch_size, 1, 1, 1)
+
+
+def open_court_poi(path, batch_size=1, normalize=True, homogeneous=False):
+    """utils/dataset.py:63-96 — json points in [0,1] -> (c-0.5)*2 -> [B,N,2] fp32."""
+    with open(path) as f:
+        try:
+            points_data = json.load(f)
+            ranges = points_data["ranges"]
+            assert ranges[0] == 1.0 and ranges[1] == 1.0
+            points = []
+            for p in points_data["points"]:
+                if normalize:
+                    x, y = (p["coords"][0] - 0.5) * 2, (p["coords"][1] - 0.5) * 2
+                else:
+                    x, y = p["coords"][0], p["coords"][1]
+                points.append((x, y, 1.0) if homogeneous else (x, y))
+            points = np.array(points)
+        except Exception as e:
+            raise ValueError(f"Cannot read {path}: {str(e)}")
+    points_tensor = torch.from_numpy(points).type(torch.FloatTensor).unsqueeze(0)
+    return points_tensor.repeat(batch_size, 1, 1)
+
+
+def load_bundled(name: str, size, num_classes: int = 4, batch_size: int = 1):
+    """Class-index templates / POI shipped with the package (generated from the reference's
+    assets by tools/make_golden.py through the reference's own loaders).
+
+    name: 'ncaa_nc4' | 'pitch_v3_nc4'; size (W,H) in {(640,360),(1280,720)}.
+    Returns (template [B,1,H,W] fp32 = class/num_classes, poi [B,N,2] fp32 in [-1,1])."""
+    z = np.load(os.path.join(DATA_DIR, "court_templates.npz"))
+    key = f"{name}_{size[0]}x{size[1]}"
+    cls = np.unpackbits(z[key + "_bits"]).reshape(-1)[: size[0] * size[1] * 2]
+    cls = (cls[0::2] * 2 + cls[1::2]).reshape(size[1], size[0]).astype(np.float64)
+    tmpl = torch.from_numpy(cls / float(num_classes)).type(torch.FloatTensor)[None, None]
+    poi = torch.from_numpy(z[name.split("_")[0] + "_poi"]).type(torch.FloatTensor)[None]
+    return tmpl.repeat(batch_size, 1, 1, 1), poi.repeat(batch_size, 1, 1)
+
+
+class CourtTemplate:
+    """A court template resident on one GPU in the layout the kernels want.
+
+    ``court_img`` is what the reference hands to ``Reconstructor`` ([B,1,Hc,Wc] or [1,1,Hc,Wc]
+    fp32, the same image repeated — utils/dataset.py:59).  If the first sample has at most 16
+    distinct values it is packed (Q2: <=4 values, Q4: <=16); otherwise the fp32 image is
+    sampled directly.  ``shared=False`` keeps per-sample fp32 templates (general kornia use).
+    """
+
+    def __init__(self, court_img: torch.Tensor, shared: bool = True, pack: bool = True):
+        if not isinstance(court_img, torch.Tensor):
+            raise TypeError("court_img must be a torch.Tensor")
+        if court_img.dtype != torch.float32:
+            raise TypeError(f"court_img must be float32, got {court_img.dtype}")
+        if not court_img.is_cuda:
+            raise TypeError("court_img must live on a CUDA device (sfh_b200 has no CPU path)")
+        if court_img.ndim != 4:
+            raise ValueError(f"court_img must be [B,C,Hc,Wc], got {tuple(court_img.shape)}")
+        self.device = court_img.device
+        self.C, self.Hc, self.Wc = court_img.shape[1:]
+        self.fmt = _lib.TMPL_F32
+        self.palette = None
+        self.pitch = 0
+        if shared:
+            self.f32 = court_img[0:1].contiguous()
+            self.batch_stride = 0
+        else:
+            self.f32 = court_img.contiguous()
+            self.batch_stride = self.C * self.Hc * self.Wc
+        self.data = self.f32
+        if shared and pack and self.C == 1:
+            self._try_pack()
+
+    def _try_pack(self):
+        vals = torch.unique(self.f32)          # one-off, at construction (host sync is fine here)
+        if vals.numel() > 16 or not torch.isfinite(vals).all():
+            return
+        pal = sorted(set([0.0] + [float(v) for v in vals.cpu().tolist()]))
+        pal.remove(0.0)
+        pal = [0.0] + pal                       # palette[0] must be the zero-padding value
+        if len(pal) > 16:
+            return
+        fmt = _lib.TMPL_Q2 if len(pal) <= 4 else _lib.TMPL_Q4
+        dt = torch.uint8 if fmt == _lib.TMPL_Q2 else torch.int16
+        pitch = (self.Wc + 1 + 15) // 16 * 16
+        packed = torch.zeros((self.Hc + 1, pitch), dtype=dt, device=self.device)
+        err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        host_pal = (C.c_float * len(pal))(*pal)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().sfh_template_pack(self.f32.data_ptr(), self.Hc, self.Wc, host_pal, len(pal),
+                                              packed.data_ptr(), pitch, fmt, err.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "sfh_template_pack")
+        if int(err.item()) != 0:
+            raise RuntimeError("sfh_template_pack: template texel not in palette")
+        self.fmt, self.palette, self.pitch, self.data = fmt, pal, pitch, packed
+
+    def desc(self) -> _lib.SfhTemplate:
+        d = _lib.SfhTemplate()
+        d.data = self.data.data_ptr()
+        d.fmt, d.channels, d.height, d.width = self.fmt, self.C, self.Hc, self.Wc
+        d.pitch = self.pitch
+        d.batch_stride = self.batch_stride
+        if self.palette is not None:
+            d.n_palette = len(self.palette)
+            for i, v in enumerate(self.palette):
+                d.palette[i] = v
+        return d

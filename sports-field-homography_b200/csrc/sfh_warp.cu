@@ -1,0 +1,634 @@
+// sfh_warp.cu — the fused warp kernel family (sm_100a) and its C-ABI launchers.
+//
+// One kernel template covers the four passes over the output pixels that the reference spreads
+// over ~20 ATen launches:
+//   kEpiStore   HomographyWarper.forward                     models/reconstructor.py:116
+//   kEpiBwd     its autograd w.r.t. theta                    train.py:235
+//   kEpiLoss    warp + MSE/SmoothL1 vs gt/nc + dL_b/dtheta   train.py:194-197, models/losses.py:35-38
+//   kEpiPredict int32(warp*nc) + CE consistency score        models/reconstructor.py:223-240
+//
+// Layout of one CTA: 8 warps x 32 lanes; a lane owns 4 consecutive output pixels of a row
+// (128-bit stores / 2x128-bit int64 loads, a warp covers 128 px = 512 B of fp32 per row); a warp
+// owns rows {w, w+8} of a 128x16 tile.  The sampling grid lives in registers only.  Per-sample
+// sums (loss, 9 dtheta terms, score) go lane -> warp shuffle -> smem -> one partial per CTA; the
+// last CTA of a sample (ticket counter, no data atomics) adds the partials in fixed order in fp64.
+#include "sfh_device.cuh"
+#include "sfh_poi.cuh"
+
+namespace sfh {
+
+struct FusedParams {
+    const float* theta;
+    const float* xs;
+    const float* ys;
+    sfh_template t;
+    int B, H, W;
+    int tiles_x, ntiles;
+    int vec4;            // W % 4 == 0 and all row bases 16-byte aligned
+    // kEpiStore / kEpiBwd
+    float* out_f;        // [B,C,H,W]
+    const float* grad_out;
+    float* dtheta;       // [B,9]
+    // kEpiLoss
+    const long long* gt;
+    int nc, kind, nc_pow2;
+    float inv_nc, invN;
+    float* Lb;
+    float* J;
+    // kEpiPredict
+    const float* logits;
+    int lh, lw, ratio;   // ratio: 1 (same size), 2 (H=2h, W=2w), 0 (score not fused)
+    int32_t* out_i;
+    float* score;
+    // POI tail block (blockIdx.x == ntiles)
+    PoiParams poi;
+    // workspace
+    int* counters;
+    float* partials;
+};
+
+// Geometry of one output pixel, everything the epilogues need.
+struct Pix {
+    Flow f;
+    float ix, iy;
+    float ex, wx, sy, ny;   // bilinear factors: ex = x1-ix, wx = ix-x0, sy = y1-iy, ny = iy-y0
+    int x0, y0;
+};
+
+template <int MODE>
+__device__ __forceinline__ Pix pixel_geom(const Homog& Hm, float pu0, float pu3, float pu6, float v,
+                                          float Wc_f, float Hc_f) {
+    Pix p;
+    p.f = flow_at(Hm, pu0, pu3, pu6, v);
+    p.ix = unnormalize(p.f.x, Wc_f);
+    p.iy = unnormalize(p.f.y, Hc_f);
+    if (MODE == SFH_MODE_NEAREST) {
+        p.x0 = __float2int_rn(p.ix);   // nearbyint: half to even
+        p.y0 = __float2int_rn(p.iy);
+        p.ex = p.wx = p.sy = p.ny = 0.f;
+    } else {
+        const float fx = floorf(p.ix), fy = floorf(p.iy);
+        p.x0 = (int)fx;
+        p.y0 = (int)fy;
+        p.ex = __fsub_rn(__fadd_rn(fx, 1.0f), p.ix);
+        p.wx = __fsub_rn(p.ix, fx);
+        p.sy = __fsub_rn(__fadd_rn(fy, 1.0f), p.iy);
+        p.ny = __fsub_rn(p.iy, fy);
+    }
+    return p;
+}
+
+// ATen accumulation order: nw, ne, sw, se, each step one FMA.
+__device__ __forceinline__ float bilerp(const Pix& p, float a, float b, float c, float d) {
+    float o = __fmul_rn(a, __fmul_rn(p.ex, p.sy));
+    o = __fmaf_rn(b, __fmul_rn(p.wx, p.sy), o);
+    o = __fmaf_rn(c, __fmul_rn(p.ex, p.ny), o);
+    o = __fmaf_rn(d, __fmul_rn(p.wx, p.ny), o);
+    return o;
+}
+
+// d(out)/d(theta) contribution of one pixel given g = dL/d(out) (already summed over channels
+// into gix/giy):  grid_sampler_2d_backward -> scale*p backward -> bmm backward.
+struct GradAcc {
+    float xu, x1, yu, y1, zu, z1;    // sums of gX*u, gX, gY*u, gY, gZ*u, gZ over the current row
+    float a[9];                      // running dtheta
+    __device__ __forceinline__ void zero() {
+        xu = x1 = yu = y1 = zu = z1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) a[k] = 0.f;
+    }
+    __device__ __forceinline__ void add(const Pix& p, float gix, float giy, float halfWc, float halfHc, float u) {
+        const float gx = gix * halfWc, gy = giy * halfHc;
+        const float gX = gx * p.f.s, gY = gy * p.f.s;
+        const float gZ = p.f.zok ? -(gx * p.f.X + gy * p.f.Y) * p.f.s * p.f.s : 0.f;
+        xu = fmaf(gX, u, xu); x1 += gX;
+        yu = fmaf(gY, u, yu); y1 += gY;
+        zu = fmaf(gZ, u, zu); z1 += gZ;
+    }
+    __device__ __forceinline__ void end_row(float v) {
+        a[0] += xu; a[1] = fmaf(x1, v, a[1]); a[2] += x1;
+        a[3] += yu; a[4] = fmaf(y1, v, a[4]); a[5] += y1;
+        a[6] += zu; a[7] = fmaf(z1, v, a[7]); a[8] += z1;
+        xu = x1 = yu = y1 = zu = z1 = 0.f;
+    }
+};
+
+// log-sum-exp cross entropy of one pixel, nc logits strided by `cs`.
+__device__ __forceinline__ float ce_pixel(const float* lg, size_t cs, int nc, int cls) {
+    float mx = -INFINITY, sel = 0.f;
+    for (int c = 0; c < nc; ++c) {
+        const float v = __ldcs(lg + c * cs);
+        mx = fmaxf(mx, v);
+        if (c == cls) sel = v;
+    }
+    float se = 0.f;
+    for (int c = 0; c < nc; ++c) se += expf(__ldg(lg + c * cs) - mx);
+    return (logf(se) + mx) - sel;
+}
+
+template <int FMT, int MODE, int EPI>
+__global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ FusedParams p) {
+    __shared__ float s_pal[16];
+    __shared__ float s_red[kWarps][kNPart];
+    __shared__ double s_fin[kNPart][kFinGroup];
+    __shared__ int s_last;
+
+    const int b = blockIdx.y, tile = blockIdx.x;
+    if ((EPI == kEpiLoss || EPI == kEpiPredict) && tile == p.ntiles) {   // POI tail block
+        poi_block(p.poi, b);
+        return;
+    }
+    if (FMT != SFH_TMPL_F32) {
+        if (threadIdx.x < 16) s_pal[threadIdx.x] = p.t.palette[threadIdx.x];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+    const int col = tx * kTileW + lane * 4;
+    const int H = p.H, W = p.W;
+    const int C = (FMT == SFH_TMPL_F32) ? p.t.channels : 1;
+
+    Homog Hm;
+    Hm.load(p.theta + 9 * b);
+    Taps<FMT> taps;
+    taps.init(p.t, b, s_pal);
+    const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
+    const float halfWc = 0.5f * Wc_f, halfHc = 0.5f * Hc_f;
+
+    // column invariants: u and the first bmm product u*h{0,3,6}
+    float u[4], pu0[4], pu3[4], pu6[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int cx = min(col + j, W - 1);
+        u[j] = p.xs ? __ldg(p.xs + cx) : mesh_coord(cx, W);
+        pu0[j] = __fmul_rn(u[j], Hm.h[0]);
+        pu3[j] = __fmul_rn(u[j], Hm.h[3]);
+        pu6[j] = __fmul_rn(u[j], Hm.h[6]);
+    }
+
+    GradAcc acc;
+    acc.zero();
+    float loss_sum = 0.f, score_sum = 0.f;
+
+#pragma unroll 1
+    for (int rr = 0; rr < kTileH / kWarps; ++rr) {
+        const int row = ty * kTileH + rr * kWarps + warp;
+        if (row >= H) continue;   // warp-uniform; lanes past W stay active (predicated)
+        const float v = p.ys ? __ldg(p.ys + row) : mesh_coord(row, H);
+        const size_t rowbase = ((size_t)b * H + row) * W + col;   // C == 1 offset
+        const bool full = p.vec4 && (col + 3 < W);
+
+        // ---- issue the streaming loads of this row first (latency overlaps the geometry) ----
+        float tgt[4];
+        if (EPI == kEpiLoss) {
+            long long g[4];
+            if (full) {
+                const longlong2 g01 = __ldcs((const longlong2*)(p.gt + rowbase));
+                const longlong2 g23 = __ldcs((const longlong2*)(p.gt + rowbase) + 1);
+                g[0] = g01.x; g[1] = g01.y; g[2] = g23.x; g[3] = g23.y;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g[j] = (col + j < W) ? __ldcs(p.gt + rowbase + j) : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float gf = (float)(int)g[j];   // class ids: low 32 bits carry the value
+                tgt[j] = p.nc_pow2 ? __fmul_rn(gf, p.inv_nc) : __fdiv_rn(gf, (float)p.nc);
+            }
+        }
+
+        Pix px[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) px[j] = pixel_geom<MODE>(Hm, pu0[j], pu3[j], pu6[j], v, Wc_f, Hc_f);
+
+        if (EPI == kEpiStore || EPI == kEpiBwd) {
+            float gix[4] = {0.f, 0.f, 0.f, 0.f}, giy[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int c = 0; c < C; ++c) {
+                const size_t off = (((size_t)b * C + c) * H + row) * W + col;
+                float o[4], go[4];
+                if (EPI == kEpiBwd) {
+                    if (full) {
+                        const float4 t4 = __ldcs((const float4*)(p.grad_out + off));
+                        go[0] = t4.x; go[1] = t4.y; go[2] = t4.z; go[3] = t4.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) go[j] = (col + j < W) ? __ldcs(p.grad_out + off + j) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (MODE == SFH_MODE_NEAREST) {
+                        o[j] = taps.fetch1(c, px[j].x0, px[j].y0);
+                    } else {
+                        float ta, tb, tc, td;
+                        taps.fetch4(c, px[j].x0, px[j].y0, ta, tb, tc, td);
+                        if (EPI == kEpiStore) o[j] = bilerp(px[j], ta, tb, tc, td);
+                        if (EPI == kEpiBwd) {
+                            gix[j] += ((tb - ta) * px[j].sy + (td - tc) * px[j].ny) * go[j];
+                            giy[j] += ((tc - ta) * px[j].ex + (td - tb) * px[j].wx) * go[j];
+                        }
+                    }
+                }
+                if (EPI == kEpiStore) {
+                    if (full) {
+                        st_stream((float4*)(p.out_f + off), make_float4(o[0], o[1], o[2], o[3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (col + j < W) p.out_f[off + j] = o[j];
+                    }
+                }
+            }
+            if (EPI == kEpiBwd) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (col + j < W) acc.add(px[j], gix[j], giy[j], halfWc, halfHc, u[j]);
+                acc.end_row(v);
+            }
+        }
+
+        if (EPI == kEpiLoss) {
+            float o[4];
+            bool any_edge = false;
+            float ta[4], tb[4], tc[4], td[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                taps.fetch4(0, px[j].x0, px[j].y0, ta[j], tb[j], tc[j], td[j]);
+                o[j] = bilerp(px[j], ta[j], tb[j], tc[j], td[j]);
+                any_edge |= (ta[j] != tb[j]) | (tc[j] != td[j]) | (ta[j] != tc[j]);
+            }
+            if (p.out_f) {
+                if (full) {
+                    st_stream((float4*)(p.out_f + rowbase), make_float4(o[0], o[1], o[2], o[3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (col + j < W) p.out_f[rowbase + j] = o[j];
+                }
+            }
+            float g[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float d = o[j] - tgt[j];
+                float l;
+                if (p.kind == SFH_LOSS_MSE) { l = d * d; g[j] = 2.0f * d; }
+                else if (fabsf(d) < 1.0f)   { l = 0.5f * d * d; g[j] = d; }
+                else                        { l = fabsf(d) - 0.5f; g[j] = d > 0.f ? 1.0f : -1.0f; }
+                if (col + j >= W) { l = 0.f; g[j] = 0.f; }
+                loss_sum += l;
+                g[j] *= p.invN;
+            }
+            // the gradient lives on footprints that straddle a class edge; a uniform footprint
+            // cancels exactly (a*sy - a*sy), so whole warps skip the chain rule when none is on one
+            if (__any_sync(0xffffffffu, any_edge)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float gix = ((tb[j] - ta[j]) * px[j].sy + (td[j] - tc[j]) * px[j].ny) * g[j];
+                    const float giy = ((tc[j] - ta[j]) * px[j].ex + (td[j] - tb[j]) * px[j].wx) * g[j];
+                    acc.add(px[j], gix, giy, halfWc, halfHc, u[j]);
+                }
+                acc.end_row(v);
+            }
+        }
+
+        if (EPI == kEpiPredict) {
+            int cls[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float o;
+                if (MODE == SFH_MODE_NEAREST) {
+                    o = taps.fetch1(0, px[j].x0, px[j].y0);
+                } else {
+                    float ta, tb, tc, td;
+                    taps.fetch4(0, px[j].x0, px[j].y0, ta, tb, tc, td);
+                    o = bilerp(px[j], ta, tb, tc, td);
+                }
+                cls[j] = __float2int_rz(__fmul_rn(o, (float)p.nc));   // (warp*nc).int()
+            }
+            if (full) {
+                st_stream((int4*)(p.out_i + rowbase), make_int4(cls[0], cls[1], cls[2], cls[3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (col + j < W) p.out_i[rowbase + j] = cls[j];
+            }
+            if (p.score && p.ratio == 1) {
+                const size_t cs = (size_t)p.lh * p.lw;
+                const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)row * p.lw + col;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (col + j < W) score_sum += ce_pixel(lg + j, cs, p.nc, cls[j]);
+            } else if (p.score && p.ratio == 2 && !(row & 1)) {
+                // F.interpolate(nearest) to (H/2, W/2) picks source pixel (2i, 2j)
+                const size_t cs = (size_t)p.lh * p.lw;
+                const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)(row >> 1) * p.lw + (col >> 1);
+                if (col < W) score_sum += ce_pixel(lg, cs, p.nc, cls[0]);
+                if (col + 2 < W) score_sum += ce_pixel(lg + 1, cs, p.nc, cls[2]);
+            }
+        }
+    }
+
+    if (EPI == kEpiStore) return;
+    if (EPI == kEpiPredict && !(p.score && p.ratio != 0)) return;
+
+    // ---------------- per-sample reduction: lane -> warp -> CTA partial -> last CTA -----------
+    float vals[kNPart];
+    vals[0] = loss_sum;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) vals[1 + k] = acc.a[k];
+    vals[10] = score_sum;
+    vals[11] = 0.f;
+#pragma unroll
+    for (int k = 0; k < kNPart - 1; ++k) {
+        if (EPI == kEpiBwd && (k == 0 || k == 10)) continue;
+        if (EPI == kEpiLoss && k == 10) continue;
+        if (EPI == kEpiPredict && k != 10) continue;
+        const float s = warp_sum(vals[k]);
+        if (lane == 0) s_red[warp][k] = s;
+    }
+    __syncthreads();
+    float* part = p.partials + ((size_t)b * p.ntiles + tile) * kNPart;
+    if (threadIdx.x < kNPart) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += s_red[w][threadIdx.x];
+        part[threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int prev = atomicAdd(p.counters + b, 1);   // ticket only; no data goes through atomics
+        s_last = (prev == p.ntiles - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {
+        const int k = threadIdx.x / kFinGroup, jj = threadIdx.x % kFinGroup;
+        if (k < kNPart) {
+            double s = 0.0;
+            const float* base = p.partials + (size_t)b * p.ntiles * kNPart + k;
+            for (int t = jj; t < p.ntiles; t += kFinGroup) s += (double)__ldcg(base + (size_t)t * kNPart);
+            s_fin[k][jj] = s;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kNPart) {
+        const int k = threadIdx.x;
+        double s = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < kFinGroup; ++jj) s += s_fin[k][jj];
+        if (EPI == kEpiBwd) {
+            if (k >= 1 && k <= 9) p.dtheta[9 * b + k - 1] = (float)s;
+        } else if (EPI == kEpiLoss) {
+            if (k == 0) p.Lb[b] = (float)(s / ((double)H * (double)W));
+            else if (k <= 9) p.J[9 * b + k - 1] = (float)s;
+        } else if (EPI == kEpiPredict) {
+            if (k == 10) p.score[b] = (float)(s / ((double)p.lh * (double)p.lw));
+        }
+    }
+    if (threadIdx.x == 0) p.counters[b] = 0;   // leave the workspace zeroed for the next call
+}
+
+// Consistency score for logits sizes the fused pass does not cover (any h,w): reads the int32
+// mask back (L2-hot) with upsample_nearest's index rule.  models/reconstructor.py:230-238.
+__global__ void __launch_bounds__(kThreads) k_consistency_generic(const int32_t* mask, const float* logits,
+                                                                  int nc, int H, int W, int lh, int lw,
+                                                                  float* score) {
+    __shared__ double s_w[kWarps];
+    const int b = blockIdx.x;
+    const size_t cs = (size_t)lh * lw;
+    const float sy = (float)H / (float)lh, sx = (float)W / (float)lw;
+    double acc = 0.0;
+    for (size_t i = threadIdx.x; i < cs; i += kThreads) {
+        const int r = (int)(i / lw), c = (int)(i % lw);
+        int sr = (lh == H) ? r : (lh == 2 * H) ? (r >> 1) : min((int)floorf(r * sy), H - 1);
+        int sc = (lw == W) ? c : (lw == 2 * W) ? (c >> 1) : min((int)floorf(c * sx), W - 1);
+        const int cls = mask[((size_t)b * H + sr) * W + sc];
+        acc += (double)ce_pixel(logits + (size_t)b * nc * cs + i, cs, nc, cls);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < kWarps; ++w) s += s_w[w];
+        score[b] = (float)(s / (double)cs);
+    }
+}
+
+// Build the quad-packed palette-index template (see sfh_template in the header).
+template <int BITS, typename T>
+__global__ void k_pack(const float* tmpl, int Hc, int Wc, T* q, int pitch, int npal,
+                       const __grid_constant__ sfh_template pal, int32_t* err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // packed column 0..Wc
+    const int j = blockIdx.y;                               // packed row    0..Hc
+    if (i > Wc) return;
+    unsigned v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int y = j - 1 + (k >> 1), x = i - 1 + (k & 1);
+        unsigned idx = 0;
+        if (x >= 0 && x < Wc && y >= 0 && y < Hc) {
+            const float t = tmpl[(size_t)y * Wc + x];
+            int found = -1;
+            for (int c = 0; c < npal; ++c) if (pal.palette[c] == t) { found = c; break; }
+            if (found < 0) { atomicExch(err, 1); found = 0; }
+            idx = (unsigned)found;
+        }
+        v |= idx << (k * BITS);
+    }
+    q[(size_t)j * pitch + i] = (T)v;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+static int check_template(const sfh_template* t) {
+    if (!t || !t->data || t->height <= 0 || t->width <= 0) return SFH_E_BADARG;
+    if (t->fmt == SFH_TMPL_F32) return t->channels >= 1 ? 0 : SFH_E_BADARG;
+    if (t->fmt == SFH_TMPL_Q2 || t->fmt == SFH_TMPL_Q4) {
+        if (t->channels != 1 || t->pitch < t->width + 1) return SFH_E_BADARG;
+        if (t->n_palette < 1 || t->n_palette > (t->fmt == SFH_TMPL_Q2 ? 4 : 16)) return SFH_E_BADARG;
+        if (t->palette[0] != 0.0f) return SFH_E_BADARG;
+        return 0;
+    }
+    return SFH_E_BADFMT;
+}
+
+static void fill_common(FusedParams& p, const float* theta, const sfh_template* t, const float* xs,
+                        const float* ys, int B, int H, int W) {
+    memset(&p, 0, sizeof(p));
+    p.theta = theta; p.xs = xs; p.ys = ys; p.t = *t;
+    p.B = B; p.H = H; p.W = W;
+    p.tiles_x = (W + kTileW - 1) / kTileW;
+    p.ntiles = p.tiles_x * ((H + kTileH - 1) / kTileH);
+}
+
+static inline bool aligned16(const void* q) { return ((uintptr_t)q & 15u) == 0; }
+
+static int setup_ws(FusedParams& p, void* ws, int64_t ws_bytes) {
+    const int64_t need = sfh_workspace_bytes(p.B, p.H, p.W);
+    if (!ws || ws_bytes < need) return SFH_E_WS;
+    p.counters = (int*)ws;
+    p.partials = (float*)((char*)ws + align_up((int64_t)p.B * 4, 256));
+    return 0;
+}
+
+template <int MODE, int EPI>
+static int launch_fused(const FusedParams& p, bool poi_tail, cudaStream_t st) {
+    dim3 grid(p.ntiles + (poi_tail ? 1 : 0), p.B), block(kThreads);
+    switch (p.t.fmt) {
+        case SFH_TMPL_F32: k_fused<SFH_TMPL_F32, MODE, EPI><<<grid, block, 0, st>>>(p); break;
+        case SFH_TMPL_Q2:  k_fused<SFH_TMPL_Q2, MODE, EPI><<<grid, block, 0, st>>>(p); break;
+        case SFH_TMPL_Q4:  k_fused<SFH_TMPL_Q4, MODE, EPI><<<grid, block, 0, st>>>(p); break;
+        default: return SFH_E_BADFMT;
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace sfh
+
+using namespace sfh;
+
+extern "C" {
+
+int sfh_abi_version(void) { return SFH_ABI_VERSION; }
+
+const char* sfh_build_info(void) {
+    return "sfh_b200 abi " "1" " sm_100a tile 128x16 threads 256 (" __DATE__ " " __TIME__ ")";
+}
+
+const char* sfh_error_string(int code) {
+    if (code == 0) return "success";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    switch (code) {
+        case SFH_E_BADARG: return "sfh: bad argument";
+        case SFH_E_BADFMT: return "sfh: unknown template format";
+        case SFH_E_BADMODE: return "sfh: unknown interpolation mode / loss kind";
+        case SFH_E_WS: return "sfh: workspace missing or too small";
+    }
+    return "sfh: unknown error";
+}
+
+int64_t sfh_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    const int64_t ntiles = (int64_t)((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+    return align_up((int64_t)B * 4, 256) + (int64_t)B * ntiles * kNPart * 4;
+}
+
+int sfh_template_pack(const float* tmpl, int Hc, int Wc, const float* palette_host, int n_palette,
+                      void* packed, int pitch, int fmt, int32_t* err_flag, void* stream) {
+    if (!tmpl || !packed || !palette_host || !err_flag || Hc <= 0 || Wc <= 0 || pitch < Wc + 1) return SFH_E_BADARG;
+    const int cap = fmt == SFH_TMPL_Q2 ? 4 : fmt == SFH_TMPL_Q4 ? 16 : 0;
+    if (!cap) return SFH_E_BADFMT;
+    if (n_palette < 1 || n_palette > cap || palette_host[0] != 0.0f) return SFH_E_BADARG;
+    sfh_template pal;
+    memset(&pal, 0, sizeof(pal));
+    for (int i = 0; i < n_palette; ++i) pal.palette[i] = palette_host[i];
+    dim3 block(128), grid((Wc + 1 + 127) / 128, Hc + 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fmt == SFH_TMPL_Q2) k_pack<2, uint8_t><<<grid, block, 0, st>>>(tmpl, Hc, Wc, (uint8_t*)packed, pitch, n_palette, pal, err_flag);
+    else                    k_pack<4, uint16_t><<<grid, block, 0, st>>>(tmpl, Hc, Wc, (uint16_t*)packed, pitch, n_palette, pal, err_flag);
+    return (int)cudaGetLastError();
+}
+
+int sfh_warp_fwd(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
+                 int B, int H, int W, int mode, float* out, void* stream) {
+    int rc = check_template(tmpl);
+    if (rc) return rc;
+    if (!theta || !out || B <= 0 || H <= 0 || W <= 0) return SFH_E_BADARG;
+    FusedParams p;
+    fill_common(p, theta, tmpl, xs, ys, B, H, W);
+    p.out_f = out;
+    p.vec4 = (W % 4 == 0) && aligned16(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == SFH_MODE_BILINEAR) return launch_fused<SFH_MODE_BILINEAR, kEpiStore>(p, false, st);
+    if (mode == SFH_MODE_NEAREST) return launch_fused<SFH_MODE_NEAREST, kEpiStore>(p, false, st);
+    return SFH_E_BADMODE;
+}
+
+int sfh_warp_bwd(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
+                 const float* grad_out, int B, int H, int W, float* dtheta,
+                 void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_template(tmpl);
+    if (rc) return rc;
+    if (!theta || !grad_out || !dtheta || B <= 0 || H <= 0 || W <= 0) return SFH_E_BADARG;
+    FusedParams p;
+    fill_common(p, theta, tmpl, xs, ys, B, H, W);
+    if ((rc = setup_ws(p, workspace, workspace_bytes))) return rc;
+    p.grad_out = grad_out; p.dtheta = dtheta;
+    p.vec4 = (W % 4 == 0) && aligned16(grad_out);
+    return launch_fused<SFH_MODE_BILINEAR, kEpiBwd>(p, false, (cudaStream_t)stream);
+}
+
+int sfh_warp_loss_fwd_bwd(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
+                          const int64_t* gt, int nc, int kind, int B, int H, int W,
+                          float* warp_out, float* L_b, float* dLb_dtheta,
+                          const float* court_poi, int64_t court_poi_bstride, int N,
+                          const float* gt_poi, const float* nonzeros, const float* num_nonzero,
+                          float* poi_out, float* R_b, float* dRb_dtheta,
+                          void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_template(tmpl);
+    if (rc) return rc;
+    if (!theta || !gt || !L_b || !dLb_dtheta || B <= 0 || H <= 0 || W <= 0 || nc <= 0) return SFH_E_BADARG;
+    if (tmpl->channels != 1) return SFH_E_BADARG;
+    if (kind != SFH_LOSS_MSE && kind != SFH_LOSS_SMOOTHL1) return SFH_E_BADMODE;
+    FusedParams p;
+    fill_common(p, theta, tmpl, xs, ys, B, H, W);
+    if ((rc = setup_ws(p, workspace, workspace_bytes))) return rc;
+    p.gt = (const long long*)gt; p.nc = nc; p.kind = kind;
+    p.nc_pow2 = (nc & (nc - 1)) == 0;
+    p.inv_nc = 1.0f / (float)nc;
+    p.invN = 1.0f / ((float)H * (float)W);
+    p.out_f = warp_out; p.Lb = L_b; p.J = dLb_dtheta;
+    p.vec4 = (W % 4 == 0) && aligned16(gt) && (!warp_out || aligned16(warp_out));
+    const bool poi_tail = court_poi != nullptr;
+    if (poi_tail) {
+        if (N <= 0 || !poi_out) return SFH_E_BADARG;
+        if (gt_poi && (!nonzeros || !num_nonzero || !R_b || !dRb_dtheta)) return SFH_E_BADARG;
+        p.poi.theta = theta; p.poi.court_poi = court_poi; p.poi.bstride = court_poi_bstride;
+        p.poi.N = N; p.poi.normalize = 1; p.poi.poi_out = poi_out;
+        p.poi.gt_poi = gt_poi; p.poi.nonzeros = nonzeros; p.poi.num_nonzero = num_nonzero;
+        p.poi.Rb = R_b; p.poi.K = dRb_dtheta;
+    }
+    return launch_fused<SFH_MODE_BILINEAR, kEpiLoss>(p, poi_tail, (cudaStream_t)stream);
+}
+
+int sfh_predict_tail(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
+                     int mode, int nc, const float* logits, int h, int w, int B, int H, int W,
+                     int32_t* warp_out, float* score,
+                     const float* court_poi, int64_t court_poi_bstride, int N, float* poi_out,
+                     void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_template(tmpl);
+    if (rc) return rc;
+    if (!theta || !warp_out || B <= 0 || H <= 0 || W <= 0 || nc <= 0) return SFH_E_BADARG;
+    if (tmpl->channels != 1) return SFH_E_BADARG;
+    if (score && (!logits || h <= 0 || w <= 0)) return SFH_E_BADARG;
+    FusedParams p;
+    fill_common(p, theta, tmpl, xs, ys, B, H, W);
+    p.nc = nc; p.out_i = warp_out;
+    p.vec4 = (W % 4 == 0) && aligned16(warp_out);
+    if (score) {
+        if ((rc = setup_ws(p, workspace, workspace_bytes))) return rc;
+        p.logits = logits; p.lh = h; p.lw = w; p.score = score;
+        p.ratio = (h == H && w == W) ? 1 : (2 * h == H && 2 * w == W) ? 2 : 0;
+    }
+    const bool poi_tail = court_poi != nullptr;
+    if (poi_tail) {
+        if (N <= 0 || !poi_out) return SFH_E_BADARG;
+        p.poi.theta = theta; p.poi.court_poi = court_poi; p.poi.bstride = court_poi_bstride;
+        p.poi.N = N; p.poi.normalize = 1; p.poi.poi_out = poi_out;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == SFH_MODE_NEAREST) rc = launch_fused<SFH_MODE_NEAREST, kEpiPredict>(p, poi_tail, st);
+    else if (mode == SFH_MODE_BILINEAR) rc = launch_fused<SFH_MODE_BILINEAR, kEpiPredict>(p, poi_tail, st);
+    else return SFH_E_BADMODE;
+    if (rc) return rc;
+    if (score && p.ratio == 0) {
+        k_consistency_generic<<<B, kThreads, 0, st>>>(warp_out, logits, nc, H, W, h, w, score);
+        rc = (int)cudaGetLastError();
+    }
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,314 @@
+"""The Reconstructor's STN warp stage on B200: same call surface, fused kernels underneath.
+
+``STNWarpStage`` owns what ``Reconstructor`` keeps as plain attributes (court_img, court_poi,
+warper — models/reconstructor.py:55-56,100-107) and exposes
+
+    warp(theta)                      == Reconstructor.warp            (:109-118)
+    transform_poi(theta)             == Reconstructor.transform_poi   (:120-130)
+    forward_tail(theta)              -> {'theta','poi','warp_mask'}   (:185-192)
+    predict_tail(theta, logits, ...) -> {'theta','warp_mask','consist_score','poi'}  (:221-245)
+    train_tail(theta, gt_masks, ...) -> fused warp + rec loss + reprojection loss with dL/dtheta
+                                        (train.py:194-197,209-214, models/losses.py)
+
+``patch_reconstructor(net)`` installs the stage into an existing reference ``Reconstructor``
+(monkey-patching ``warp`` / ``transform_poi`` / the predict tail) without adding state_dict keys.
+"""
+from __future__ import annotations
+
+import types
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .court import CourtTemplate
+from .warper import HomographyWarper, _WS, _ptr, _stream, check_theta
+
+
+def _check_f32_cuda(t: torch.Tensor, name: str, device) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if t.device != device:
+        raise TypeError(f"{name} must be on {device}, got {t.device}")
+    return t.contiguous()
+
+
+class _PoiFn(torch.autograd.Function):
+    """poi = transform_points(inverse(theta), court_poi) [/2+0.5] with dtheta backward."""
+
+    @staticmethod
+    def forward(ctx, theta9, court_poi, bstride, normalize):
+        B, N = theta9.shape[0], court_poi.shape[1]
+        out = torch.empty((B, N, 2), dtype=torch.float32, device=theta9.device)
+        with torch.cuda.device(theta9.device):
+            rc = _lib.lib().sfh_poi_fwd(theta9.data_ptr(), court_poi.data_ptr(), bstride, B, N,
+                                        int(normalize), out.data_ptr(), _stream())
+        _lib.check(rc, "sfh_poi_fwd")
+        ctx.save_for_backward(theta9, court_poi)
+        ctx.bstride, ctx.normalize = bstride, normalize
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        theta9, court_poi = ctx.saved_tensors
+        B, N = theta9.shape[0], court_poi.shape[1]
+        g = g.contiguous()
+        dth = torch.empty_like(theta9)
+        with torch.cuda.device(theta9.device):
+            rc = _lib.lib().sfh_poi_bwd(theta9.data_ptr(), court_poi.data_ptr(), ctx.bstride, g.data_ptr(),
+                                        B, N, int(ctx.normalize), dth.data_ptr(), _stream())
+        _lib.check(rc, "sfh_poi_bwd")
+        return dth, None, None, None
+
+
+class _TrainTailFn(torch.autograd.Function):
+    """One launch: warp_mask, L_b (rec loss per sample), poi, R_b (reprojection per sample) and
+    the Jacobians J_b = dL_b/dtheta_b, K_b = dR_b/dtheta_b.  Backward is a scaled add."""
+
+    @staticmethod
+    def forward(ctx, theta9, stage, gt_masks, kind, want_mask, gt_poi, nonzeros, num_nonzero):
+        B = theta9.shape[0]
+        H, W = stage.height, stage.width
+        dev = theta9.device
+        tmpl = stage.template
+        warp_out = torch.empty((B, H, W), dtype=torch.float32, device=dev) if want_mask else None
+        Lb = torch.empty(B, dtype=torch.float32, device=dev)
+        J = torch.empty((B, 9), dtype=torch.float32, device=dev)
+        with_poi = stage.court_poi is not None
+        with_rep = with_poi and gt_poi is not None
+        N = stage.court_poi.shape[1] if with_poi else 0
+        poi = torch.empty((B, N, 2), dtype=torch.float32, device=dev) if with_poi else None
+        Rb = torch.empty(B, dtype=torch.float32, device=dev) if with_rep else None
+        K = torch.empty((B, 9), dtype=torch.float32, device=dev) if with_rep else None
+        xs, ys = stage.warper.grid_factors(dev)
+        ws = _WS.get(dev, B, H, W)
+        d = tmpl.desc()
+        with torch.cuda.device(dev):
+            rc = _lib.lib().sfh_warp_loss_fwd_bwd(
+                theta9.data_ptr(), d, xs.data_ptr(), ys.data_ptr(), gt_masks.data_ptr(),
+                stage.mask_classes, _lib.LOSS[kind], B, H, W,
+                _ptr(warp_out), Lb.data_ptr(), J.data_ptr(),
+                _ptr(stage.court_poi) if with_poi else None, stage.poi_bstride, N,
+                _ptr(gt_poi) if with_rep else None, _ptr(nonzeros) if with_rep else None,
+                _ptr(num_nonzero) if with_rep else None,
+                _ptr(poi), _ptr(Rb), _ptr(K), ws.data_ptr(), ws.numel(), _stream())
+        _lib.check(rc, "sfh_warp_loss_fwd_bwd")
+        ctx.save_for_backward(theta9, J, K if with_rep else J)
+        ctx.with_rep, ctx.with_poi, ctx.stage = with_rep, with_poi, stage
+        ctx.set_materialize_grads(False)       # unused outputs arrive as None: no zero-fill, no sync
+        outs = (warp_out if want_mask else Lb.new_empty(0), Lb,
+                poi if with_poi else Lb.new_empty(0), Rb if with_rep else Lb.new_empty(0))
+        ctx.mark_non_differentiable(outs[0])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_mask, g_Lb, g_poi, g_Rb):
+        theta9, J, K = ctx.saved_tensors
+        dth = torch.zeros_like(J) if g_Lb is None else g_Lb.reshape(-1, 1).to(torch.float32) * J
+        if ctx.with_rep and g_Rb is not None:
+            dth = dth + g_Rb.reshape(-1, 1).to(torch.float32) * K
+        if ctx.with_poi and g_poi is not None:
+            # poi was also used outside the fused reprojection loss: generic POI backward
+            st = ctx.stage
+            extra = torch.empty_like(theta9)
+            B, N = theta9.shape[0], st.court_poi.shape[1]
+            with torch.cuda.device(theta9.device):
+                rc = _lib.lib().sfh_poi_bwd(theta9.data_ptr(), st.court_poi.data_ptr(), st.poi_bstride,
+                                            g_poi.contiguous().data_ptr(), B, N, 1, extra.data_ptr(), _stream())
+            _lib.check(rc, "sfh_poi_bwd")
+            dth = dth + extra
+        return dth, None, None, None, None, None, None, None
+
+
+class STNWarpStage(torch.nn.Module):
+    """B200 implementation of the warp stage of ``Reconstructor`` for a fixed court template.
+
+    Arguments mirror the corresponding ``Reconstructor.__init__`` ones
+    (models/reconstructor.py:36-49): ``court_img`` [B,1,Hc,Wc] fp32 CUDA, ``court_poi`` [B,N,2]
+    fp32 CUDA in [-1,1] (or None), ``warp_size`` (W,H), ``mask_classes``, ``warp_with_nearest``.
+    """
+
+    def __init__(self, court_img: torch.Tensor, court_poi: Optional[torch.Tensor] = None,
+                 warp_size=(640, 360), mask_classes: int = 4, warp_with_nearest: bool = False):
+        super().__init__()
+        self.width, self.height = int(warp_size[0]), int(warp_size[1])
+        self.mask_classes = int(mask_classes)
+        self.mode = "nearest" if warp_with_nearest else "bilinear"
+        # plain attributes, like the reference: nothing enters state_dict()
+        self.court_img = court_img
+        self.warper = HomographyWarper(self.height, self.width, mode=self.mode)
+        self.template: CourtTemplate = self.warper.set_template(court_img)
+        self.device = court_img.device
+        if court_poi is not None:
+            court_poi = _check_f32_cuda(court_poi, "court_poi", self.device)
+            if court_poi.ndim != 3 or court_poi.shape[-1] != 2:
+                raise ValueError(f"court_poi must be [B,N,2], got {tuple(court_poi.shape)}")
+        self.court_poi = court_poi
+        self.poi_bstride = 0 if court_poi is None or court_poi.shape[0] == 1 else court_poi.shape[1] * 2
+
+    # ------------------------------------------------------------------ reference-named methods
+    def warp(self, theta: torch.Tensor, court_img: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Reconstructor.warp (models/reconstructor.py:109-118): [B,H,W] fp32."""
+        theta9 = check_theta(theta, self.device)
+        src = self.court_img if court_img is None else court_img
+        bs = theta9.shape[0]
+        if src.shape[0] > bs:
+            src = src[0:bs]                       # template = court_img[0:bs]  (:114)
+        return self.warper(src, theta9.view(-1, 3, 3)).squeeze(1)
+
+    def transform_poi(self, theta: torch.Tensor, court_poi: Optional[torch.Tensor] = None,
+                      normalize: bool = True) -> torch.Tensor:
+        """Reconstructor.transform_poi (models/reconstructor.py:120-130): [B,N,2] fp32 in [0,1]."""
+        theta9 = check_theta(theta, self.device)
+        poi = self.court_poi if court_poi is None else _check_f32_cuda(court_poi, "court_poi", self.device)
+        if poi is None:
+            raise ValueError("no court_poi given")
+        bstride = 0 if poi.shape[0] == 1 else poi.shape[1] * 2
+        if bstride and poi.shape[0] < theta9.shape[0]:
+            raise ValueError("batch larger than the number of court_poi rows")
+        return _PoiFn.apply(theta9, poi, bstride, normalize)
+
+    def forward_tail(self, theta: torch.Tensor) -> dict:
+        """Warp-stage part of Reconstructor.forward (models/reconstructor.py:185-192)."""
+        ret = {"theta": theta}
+        if self.court_poi is not None:
+            ret["poi"] = self.transform_poi(theta)
+        ret["warp_mask"] = self.warp(theta)
+        return ret
+
+    forward = forward_tail
+
+    @torch.no_grad()
+    def predict_tail(self, theta: torch.Tensor, logits: Optional[torch.Tensor] = None,
+                     consistency: bool = True, project_poi: bool = False) -> dict:
+        """Warp-stage part of Reconstructor.predict (models/reconstructor.py:221-245):
+        int32 warp_mask (= warp*mask_classes), consist_score [B], optional poi — one launch."""
+        theta9 = check_theta(theta, self.device)
+        B, H, W = theta9.shape[0], self.height, self.width
+        ret = {"theta": theta}
+        score = None
+        h = w = 0
+        if consistency and logits is not None:
+            logits = _check_f32_cuda(logits, "logits", self.device)
+            if logits.ndim != 4 or logits.shape[0] != B or logits.shape[1] != self.mask_classes:
+                raise ValueError(f"logits must be [B,{self.mask_classes},h,w], got {tuple(logits.shape)}")
+            h, w = logits.shape[2:]
+            score = torch.empty(B, dtype=torch.float32, device=self.device)
+        want_poi = project_poi and self.court_poi is not None
+        N = self.court_poi.shape[1] if want_poi else 0
+        poi = torch.empty((B, N, 2), dtype=torch.float32, device=self.device) if want_poi else None
+        mask = torch.empty((B, H, W), dtype=torch.int32, device=self.device)
+        xs, ys = self.warper.grid_factors(self.device)
+        ws = _WS.get(self.device, B, H, W)
+        d = self.template.desc()
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().sfh_predict_tail(
+                theta9.data_ptr(), d, xs.data_ptr(), ys.data_ptr(), _lib.MODE[self.mode],
+                self.mask_classes, _ptr(logits) if score is not None else None, h, w, B, H, W,
+                mask.data_ptr(), _ptr(score),
+                _ptr(self.court_poi) if want_poi else None, self.poi_bstride, N, _ptr(poi),
+                ws.data_ptr(), ws.numel(), _stream())
+        _lib.check(rc, "sfh_predict_tail")
+        ret["warp_mask"] = mask
+        if score is not None:
+            ret["consist_score"] = score
+        if want_poi:
+            ret["poi"] = poi
+        return ret
+
+    def train_tail(self, theta: torch.Tensor, gt_masks: torch.Tensor, rec_loss: str = "MSE",
+                   gt_poi: Optional[torch.Tensor] = None, nonzeros: Optional[torch.Tensor] = None,
+                   num_nonzero: Optional[torch.Tensor] = None, want_mask: bool = True) -> dict:
+        """Fused training tail.  Returns per-sample terms so the caller applies the reference's own
+        weighting / reduction (models/losses.py:38-39 broadcasting quirk included):
+
+            rec_per_sample    [B]  = mean_{h,w} crit(warp_mask, gt_masks/nc)     (train.py:195-196)
+            reproj_per_sample [B]  = sum_n ||gt_poi-poi|| nonzeros / num_nonzero (models/losses.py:10-11)
+            warp_mask [B,H,W] fp32 (no gradient flows through it on this path), poi [B,N,2]
+        """
+        if self.mode != "bilinear":
+            raise ValueError("train_tail needs a bilinear warper (nearest has no gradient)")
+        if rec_loss not in _lib.LOSS:
+            raise NotImplementedError(rec_loss)
+        theta9 = check_theta(theta, self.device)
+        B = theta9.shape[0]
+        if gt_masks.dtype != torch.int64 or gt_masks.device != self.device:
+            raise TypeError("gt_masks must be an int64 tensor on the stage's device (utils/dataset.py:167)")
+        if tuple(gt_masks.shape) != (B, self.height, self.width):
+            raise ValueError(f"gt_masks must be [B,{self.height},{self.width}], got {tuple(gt_masks.shape)}")
+        gt_masks = gt_masks.contiguous()
+        if gt_poi is not None:
+            if self.court_poi is None:
+                raise ValueError("gt_poi given but the stage has no court_poi")
+            N = self.court_poi.shape[1]
+            gt_poi = _check_f32_cuda(gt_poi, "gt_poi", self.device)
+            nonzeros = _check_f32_cuda(nonzeros, "nonzeros", self.device)
+            num_nonzero = _check_f32_cuda(num_nonzero, "num_nonzero", self.device)
+            if tuple(gt_poi.shape) != (B, N, 2) or tuple(nonzeros.shape) != (B, N) or num_nonzero.numel() != B:
+                raise ValueError("gt_poi/nonzeros/num_nonzero shapes must be [B,N,2]/[B,N]/[B]")
+        mask, Lb, poi, Rb = _TrainTailFn.apply(theta9, self, gt_masks, rec_loss, want_mask,
+                                               gt_poi, nonzeros, num_nonzero)
+        ret = {"theta": theta, "rec_per_sample": Lb}
+        if want_mask:
+            ret["warp_mask"] = mask
+        if self.court_poi is not None:
+            ret["poi"] = poi
+        if gt_poi is not None:
+            ret["reproj_per_sample"] = Rb
+        return ret
+
+
+# ---------------------------------------------------------------------------------- drop-in
+def patch_reconstructor(net, court_img: Optional[torch.Tensor] = None,
+                        court_poi: Optional[torch.Tensor] = None) -> STNWarpStage:
+    """Swap the warp stage of a reference ``Reconstructor`` instance for the B200 kernels.
+
+    ``net.warp`` / ``net.transform_poi`` keep their signatures (models/reconstructor.py:109,120);
+    ``net.predict`` keeps its signature and result dict (:196-247) but runs the fused tail.  No
+    parameter or buffer is registered, so checkpoints keep loading with strict=True."""
+    court_img = net.court_img if court_img is None else court_img
+    court_poi = net.court_poi if court_poi is None else court_poi
+    w = net.warper
+    stage = STNWarpStage(court_img, court_poi, warp_size=(w.width, w.height),
+                         mask_classes=net.mask_classes, warp_with_nearest=(w.mode == "nearest"))
+    object.__setattr__(net, "_sfh_stage", stage)      # bypass nn.Module registration
+
+    def warp(self, theta, court_img):
+        return stage.warp(theta, court_img)
+
+    def transform_poi(self, theta, court_poi, normalize=True):
+        return stage.transform_poi(theta, court_poi, normalize)
+
+    def predict(self, x, consistency=True, project_poi=False):
+        ret = {}
+        if self.use_unet:
+            ret["logits"], _, _ = self.forward_unet(x)
+        if self.use_resnet:
+            from models.reconstructor import Input   # the reference's own enum
+            if self.resnet_input == Input.IMG:
+                y = x
+            elif self.resnet_input == Input.MASK:
+                y = ret["logits"]
+            elif self.resnet_input == Input.IMG_AND_MASK:
+                y = torch.cat((ret["logits"], x), 1)
+            else:
+                raise NotImplementedError
+            theta = self.resnet_reg(y)
+            ret["theta"] = theta
+            if self.warper is not None:
+                tail = stage.predict_tail(theta, ret.get("logits") if (consistency and self.use_unet) else None,
+                                          consistency=consistency and self.use_unet, project_poi=project_poi)
+                for k in ("warp_mask", "consist_score", "poi"):
+                    if k in tail:
+                        ret[k] = tail[k]
+            elif project_poi:
+                ret["poi"] = stage.transform_poi(theta, None)
+        return ret
+
+    net.warp = types.MethodType(warp, net)
+    net.transform_poi = types.MethodType(transform_poi, net)
+    net.predict = types.MethodType(predict, net)
+    return stage
