@@ -88,33 +88,76 @@ int sfh_warp_bwd(const float* theta, const sfh_template* tmpl, const float* xs, 
                  const float* grad_out, int B, int H, int W, float* dtheta,
                  void* workspace, int64_t workspace_bytes, void* stream);
 
-/* Fused training tail, one pass over the pixels:
+/* Fused training tail, one pass over the pixels, ONE launch:
  *   warp_mask = warp(theta)                               models/reconstructor.py:191
  *   L_b = mean_{h,w} crit(warp_mask, gt/nc)               train.py:194-197, models/losses.py:35-38
  *   J_b = dL_b/dtheta_b
- * and, when court_poi != NULL, in the same launch:
+ * when court_poi != NULL also
  *   poi = transform_poi(theta, court_poi)                 models/reconstructor.py:186,120-130
- *   R_b = sum_n ||gt_poi-poi|| * nonzeros / num_nonzero   models/losses.py:10-11
+ *   R_b = sum_n ||gt_poi-poi|| * nonzeros / num_nonzero   models/losses.py:10-11   (if gt_poi)
  *   K_b = dR_b/dtheta_b
- * gt [B,H,W] int64 (utils/dataset.py:167).  warp_out (fp32 [B,H,W]) and the reprojection
- * arguments are nullable.  Template must have C == 1. */
-int sfh_warp_loss_fwd_bwd(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
-                          const int64_t* gt, int nc, int kind, int B, int H, int W,
-                          float* warp_out, float* L_b, float* dLb_dtheta,
-                          const float* court_poi, int64_t court_poi_bstride, int N,
-                          const float* gt_poi, const float* nonzeros, const float* num_nonzero,
-                          float* poi_out, float* R_b, float* dRb_dtheta,
-                          void* workspace, int64_t workspace_bytes, void* stream);
+ * and when loss_out != NULL the reference's weighting and batch means as well
+ *   loss   = rec_lambda * mean(L_b * w) + reproj_lambda * mean(R_b)   models/losses.py:38-39,13-14
+ *   dtheta = dloss/dtheta                                            train.py:196,213,235
+ * with w = weights[b] (weights_outer == 0) or, for weights that arrived as [B,1], the
+ * reference's [B]*[B,1] -> [B,B] broadcast, i.e. w = mean(weights) (weights_outer == 1). */
+typedef struct sfh_train_tail_args {
+    const float*   theta;            /* [B,3,3] */
+    const float*   xs;               /* [W] nullable */
+    const float*   ys;               /* [H] nullable */
+    const int64_t* gt;               /* [B,H,W] int64 class ids (utils/dataset.py:167) */
+    int32_t B, H, W;
+    int32_t nc;                      /* mask_classes */
+    int32_t kind;                    /* SFH_LOSS_* */
+    int32_t N;                       /* points per sample */
+    float*  warp_out;                /* [B,H,W] fp32, nullable */
+    float*  L_b;                     /* [B] */
+    float*  dLb_dtheta;              /* [B,3,3] */
+    const float* court_poi;          /* [*,N,2] in [-1,1], nullable */
+    int64_t court_poi_bstride;       /* elements between samples, 0 = shared */
+    const float* gt_poi;             /* [B,N,2] nullable */
+    const float* nonzeros;           /* [B,N] */
+    const float* num_nonzero;        /* [B] */
+    float*  poi_out;                 /* [B,N,2] */
+    float*  R_b;                     /* [B] */
+    float*  dRb_dtheta;              /* [B,3,3] */
+    const void* weights;             /* [B] fp32/fp64, nullable (w = 1) */
+    int32_t weights_f64;
+    int32_t weights_outer;
+    float   rec_lambda;
+    float   reproj_lambda;
+    float*  loss_out;                /* scalar, nullable */
+    float*  dtheta_total;            /* [B,3,3], required with loss_out */
+    void*   workspace;
+    int64_t workspace_bytes;
+} sfh_train_tail_args;
 
-/* Reconstructor.predict tail — models/reconstructor.py:221-245:
+int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* args, void* stream);
+
+/* Reconstructor.predict tail — models/reconstructor.py:221-245, ONE launch:
  *   warp_out = int32(warp(theta) * nc)            [B,H,W]
  *   score_b  = mean CE(logits, int64(resize_nearest(warp*nc)))   logits [B,nc,h,w]  (nullable)
  *   poi_out  = transform_poi(theta, court_poi)    (nullable) */
-int sfh_predict_tail(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
-                     int mode, int nc, const float* logits, int h, int w, int B, int H, int W,
-                     int32_t* warp_out, float* score,
-                     const float* court_poi, int64_t court_poi_bstride, int N, float* poi_out,
-                     void* workspace, int64_t workspace_bytes, void* stream);
+typedef struct sfh_predict_tail_args {
+    const float* theta;
+    const float* xs;
+    const float* ys;
+    int32_t B, H, W;
+    int32_t mode;                    /* SFH_MODE_* */
+    int32_t nc;
+    int32_t h, w;                    /* logits spatial size */
+    int32_t N;
+    const float* logits;             /* [B,nc,h,w] nullable */
+    int32_t* warp_out;               /* [B,H,W] int32 */
+    float*  score;                   /* [B] nullable */
+    const float* court_poi;          /* nullable */
+    int64_t court_poi_bstride;
+    float*  poi_out;                 /* [B,N,2] */
+    void*   workspace;
+    int64_t workspace_bytes;
+} sfh_predict_tail_args;
+
+int sfh_predict_tail(const sfh_template* tmpl, const sfh_predict_tail_args* args, void* stream);
 
 /* Reconstructor.transform_poi — models/reconstructor.py:120-130:
  * poi = transform_points(inverse(theta), court_poi) [/2 + 0.5 if normalize].  fp64 inside. */

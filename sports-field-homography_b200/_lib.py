@@ -30,6 +30,31 @@ class SfhTemplate(C.Structure):
                 ("n_palette", C.c_int32), ("batch_stride", C.c_int64), ("palette", C.c_float * 16)]
 
 
+class SfhTrainTailArgs(C.Structure):
+    """struct sfh_train_tail_args (include/sfh_b200.h)."""
+    _fields_ = [("theta", C.c_void_p), ("xs", C.c_void_p), ("ys", C.c_void_p), ("gt", C.c_void_p),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("nc", C.c_int32),
+                ("kind", C.c_int32), ("N", C.c_int32),
+                ("warp_out", C.c_void_p), ("L_b", C.c_void_p), ("dLb_dtheta", C.c_void_p),
+                ("court_poi", C.c_void_p), ("court_poi_bstride", C.c_int64),
+                ("gt_poi", C.c_void_p), ("nonzeros", C.c_void_p), ("num_nonzero", C.c_void_p),
+                ("poi_out", C.c_void_p), ("R_b", C.c_void_p), ("dRb_dtheta", C.c_void_p),
+                ("weights", C.c_void_p), ("weights_f64", C.c_int32), ("weights_outer", C.c_int32),
+                ("rec_lambda", C.c_float), ("reproj_lambda", C.c_float),
+                ("loss_out", C.c_void_p), ("dtheta_total", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+
+
+class SfhPredictTailArgs(C.Structure):
+    """struct sfh_predict_tail_args (include/sfh_b200.h)."""
+    _fields_ = [("theta", C.c_void_p), ("xs", C.c_void_p), ("ys", C.c_void_p),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("mode", C.c_int32),
+                ("nc", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("N", C.c_int32),
+                ("logits", C.c_void_p), ("warp_out", C.c_void_p), ("score", C.c_void_p),
+                ("court_poi", C.c_void_p), ("court_poi_bstride", C.c_int64), ("poi_out", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _L = C.c_int64
@@ -44,10 +69,8 @@ SIGNATURES = {
     "sfh_template_pack": (_I, [_P, _I, _I, C.POINTER(C.c_float), _I, _P, _I, _I, _P, _P]),
     "sfh_warp_fwd": (_I, [_P, _T, _P, _P, _I, _I, _I, _I, _P, _P]),
     "sfh_warp_bwd": (_I, [_P, _T, _P, _P, _P, _I, _I, _I, _P, _P, _L, _P]),
-    "sfh_warp_loss_fwd_bwd": (_I, [_P, _T, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P,
-                                   _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
-    "sfh_predict_tail": (_I, [_P, _T, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P,
-                              _P, _L, _I, _P, _P, _L, _P]),
+    "sfh_warp_loss_fwd_bwd": (_I, [_T, C.POINTER(SfhTrainTailArgs), _P]),
+    "sfh_predict_tail": (_I, [_T, C.POINTER(SfhPredictTailArgs), _P]),
     "sfh_poi_fwd": (_I, [_P, _P, _L, _I, _I, _I, _P, _P]),
     "sfh_poi_bwd": (_I, [_P, _P, _L, _P, _I, _I, _I, _P, _P]),
     "sfh_transform_points_fwd": (_I, [_P, _I, _P, _I, _I, _P, _P]),

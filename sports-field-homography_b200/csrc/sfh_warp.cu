@@ -35,6 +35,15 @@ struct FusedParams {
     float inv_nc, invN;
     float* Lb;
     float* J;
+    // optional in-kernel weighting + batch reduction of the training loss (models/losses.py:38-39,
+    // train.py:196,213):  loss = rec_lambda*mean(L_b*w) + reproj_lambda*mean(R_b), dtheta = dloss/dtheta
+    const void* weights;  // [B] fp32 or fp64, nullable (=> w = 1)
+    int w_f64, w_outer;   // w_outer: weights came as [B,1] => the reference's [B,B] broadcast, w_eff = mean(w)
+    float rec_lambda, reproj_lambda;
+    float* loss_out;      // scalar, nullable: enables the combine stage
+    float* dtheta_total;  // [B,9]
+    double* contrib;      // workspace [B]
+    int arrivals;         // CTAs taking a ticket per sample
     // kEpiPredict
     const float* logits;
     int lh, lw, ratio;   // ratio: 1 (same size), 2 (H=2h, W=2w), 0 (score not fused)
@@ -134,18 +143,19 @@ __global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ Fuse
     __shared__ int s_last;
 
     const int b = blockIdx.y, tile = blockIdx.x;
-    if ((EPI == kEpiLoss || EPI == kEpiPredict) && tile == p.ntiles) {   // POI tail block
+    const int H = p.H, W = p.W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool poi_blk = (EPI == kEpiLoss || EPI == kEpiPredict) && tile == p.ntiles;
+    if (poi_blk) {                       // POI tail CTA: first warp does the 52/33 points in fp64
         poi_block(p.poi, b);
-        return;
-    }
+        if (EPI != kEpiLoss) return;     // in the training pass it also takes a ticket below
+    } else {
     if (FMT != SFH_TMPL_F32) {
         if (threadIdx.x < 16) s_pal[threadIdx.x] = p.t.palette[threadIdx.x];
         __syncthreads();
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     const int col = tx * kTileW + lane * 4;
-    const int H = p.H, W = p.W;
     const int C = (FMT == SFH_TMPL_F32) ? p.t.channels : 1;
 
     Homog Hm;
@@ -351,11 +361,13 @@ __global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ Fuse
         for (int w = 0; w < kWarps; ++w) s += s_red[w][threadIdx.x];
         part[threadIdx.x] = s;
     }
+    }   // !poi_blk
+
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const int prev = atomicAdd(p.counters + b, 1);   // ticket only; no data goes through atomics
-        s_last = (prev == p.ntiles - 1);
+        s_last = (prev == p.arrivals - 1);
     }
     __syncthreads();
     if (!s_last) return;
@@ -378,10 +390,50 @@ __global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ Fuse
         if (EPI == kEpiBwd) {
             if (k >= 1 && k <= 9) p.dtheta[9 * b + k - 1] = (float)s;
         } else if (EPI == kEpiLoss) {
-            if (k == 0) p.Lb[b] = (float)(s / ((double)H * (double)W));
+            if (k == 0) { s = s / ((double)H * (double)W); p.Lb[b] = (float)s; }
             else if (k <= 9) p.J[9 * b + k - 1] = (float)s;
+            s_fin[k][0] = s;
         } else if (EPI == kEpiPredict) {
             if (k == 10) p.score[b] = (float)(s / ((double)p.lh * (double)p.lw));
+        }
+    }
+    if (EPI == kEpiLoss && p.loss_out) {
+        // ---- weighting + batch mean + total dtheta, still inside the same launch ------------
+        __syncthreads();
+        if (warp == 0) {
+            const int B = p.B;
+            double w_eff = 1.0;
+            if (p.weights) {
+                if (p.w_outer) {            // [B]*[B,1] -> [B,B] broadcast quirk: every sample sees mean(w)
+                    double sw = 0.0;
+                    for (int i = lane; i < B; i += 32)
+                        sw += p.w_f64 ? ((const double*)p.weights)[i] : (double)((const float*)p.weights)[i];
+                    w_eff = warp_sum(sw) / (double)B;
+                } else {
+                    w_eff = p.w_f64 ? ((const double*)p.weights)[b] : (double)((const float*)p.weights)[b];
+                }
+            }
+            const bool rep = p.poi.gt_poi != nullptr;
+            const double cr = (double)p.rec_lambda * w_eff, cp = (double)p.reproj_lambda;
+            if (lane < 9) {
+                const double Kk = rep ? (double)__ldcg(p.poi.K + 9 * b + lane) : 0.0;
+                p.dtheta_total[9 * b + lane] = (float)((cr * s_fin[1 + lane][0] + cp * Kk) / (double)B);
+            }
+            int last2 = 0;
+            if (lane == 0) {
+                const double Rv = rep ? (double)__ldcg(p.poi.Rb + b) : 0.0;
+                p.contrib[b] = cr * s_fin[0][0] + cp * Rv;
+                __threadfence();
+                last2 = (atomicAdd(p.counters + B, 1) == B - 1);
+            }
+            last2 = __shfl_sync(0xffffffffu, last2, 0);
+            if (last2) {                    // last sample of the batch: fixed-order sum over b
+                __threadfence();
+                double s = 0.0;
+                for (int i = lane; i < B; i += 32) s += __ldcg(p.contrib + i);
+                s = warp_sum(s);
+                if (lane == 0) { *p.loss_out = (float)(s / (double)B); p.counters[B] = 0; }
+            }
         }
     }
     if (threadIdx.x == 0) p.counters[b] = 0;   // leave the workspace zeroed for the next call
@@ -469,8 +521,10 @@ static inline bool aligned16(const void* q) { return ((uintptr_t)q & 15u) == 0; 
 static int setup_ws(FusedParams& p, void* ws, int64_t ws_bytes) {
     const int64_t need = sfh_workspace_bytes(p.B, p.H, p.W);
     if (!ws || ws_bytes < need) return SFH_E_WS;
-    p.counters = (int*)ws;
-    p.partials = (float*)((char*)ws + align_up((int64_t)p.B * 4, 256));
+    p.counters = (int*)ws;                                             // [B+1]
+    p.contrib = (double*)((char*)ws + align_up((int64_t)(p.B + 1) * 4, 256));   // [B]
+    p.partials = (float*)((char*)p.contrib + align_up((int64_t)p.B * 8, 256));
+    p.arrivals = p.ntiles;
     return 0;
 }
 
@@ -513,7 +567,7 @@ const char* sfh_error_string(int code) {
 int64_t sfh_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     const int64_t ntiles = (int64_t)((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
-    return align_up((int64_t)B * 4, 256) + (int64_t)B * ntiles * kNPart * 4;
+    return align_up((int64_t)(B + 1) * 4, 256) + align_up((int64_t)B * 8, 256) + (int64_t)B * ntiles * kNPart * 4;
 }
 
 int sfh_template_pack(const float* tmpl, int Hc, int Wc, const float* palette_host, int n_palette,
@@ -561,71 +615,67 @@ int sfh_warp_bwd(const float* theta, const sfh_template* tmpl, const float* xs, 
     return launch_fused<SFH_MODE_BILINEAR, kEpiBwd>(p, false, (cudaStream_t)stream);
 }
 
-int sfh_warp_loss_fwd_bwd(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
-                          const int64_t* gt, int nc, int kind, int B, int H, int W,
-                          float* warp_out, float* L_b, float* dLb_dtheta,
-                          const float* court_poi, int64_t court_poi_bstride, int N,
-                          const float* gt_poi, const float* nonzeros, const float* num_nonzero,
-                          float* poi_out, float* R_b, float* dRb_dtheta,
-                          void* workspace, int64_t workspace_bytes, void* stream) {
+int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* a, void* stream) {
     int rc = check_template(tmpl);
     if (rc) return rc;
-    if (!theta || !gt || !L_b || !dLb_dtheta || B <= 0 || H <= 0 || W <= 0 || nc <= 0) return SFH_E_BADARG;
+    if (!a || !a->theta || !a->gt || !a->L_b || !a->dLb_dtheta || a->B <= 0 || a->H <= 0 || a->W <= 0 || a->nc <= 0)
+        return SFH_E_BADARG;
     if (tmpl->channels != 1) return SFH_E_BADARG;
-    if (kind != SFH_LOSS_MSE && kind != SFH_LOSS_SMOOTHL1) return SFH_E_BADMODE;
+    if (a->kind != SFH_LOSS_MSE && a->kind != SFH_LOSS_SMOOTHL1) return SFH_E_BADMODE;
+    if (a->loss_out && !a->dtheta_total) return SFH_E_BADARG;
     FusedParams p;
-    fill_common(p, theta, tmpl, xs, ys, B, H, W);
-    if ((rc = setup_ws(p, workspace, workspace_bytes))) return rc;
-    p.gt = (const long long*)gt; p.nc = nc; p.kind = kind;
-    p.nc_pow2 = (nc & (nc - 1)) == 0;
-    p.inv_nc = 1.0f / (float)nc;
-    p.invN = 1.0f / ((float)H * (float)W);
-    p.out_f = warp_out; p.Lb = L_b; p.J = dLb_dtheta;
-    p.vec4 = (W % 4 == 0) && aligned16(gt) && (!warp_out || aligned16(warp_out));
-    const bool poi_tail = court_poi != nullptr;
+    fill_common(p, a->theta, tmpl, a->xs, a->ys, a->B, a->H, a->W);
+    if ((rc = setup_ws(p, a->workspace, a->workspace_bytes))) return rc;
+    p.gt = (const long long*)a->gt; p.nc = a->nc; p.kind = a->kind;
+    p.nc_pow2 = (a->nc & (a->nc - 1)) == 0;
+    p.inv_nc = 1.0f / (float)a->nc;
+    p.invN = 1.0f / ((float)a->H * (float)a->W);
+    p.out_f = a->warp_out; p.Lb = a->L_b; p.J = a->dLb_dtheta;
+    p.vec4 = (a->W % 4 == 0) && aligned16(a->gt) && (!a->warp_out || aligned16(a->warp_out));
+    const bool poi_tail = a->court_poi != nullptr;
     if (poi_tail) {
-        if (N <= 0 || !poi_out) return SFH_E_BADARG;
-        if (gt_poi && (!nonzeros || !num_nonzero || !R_b || !dRb_dtheta)) return SFH_E_BADARG;
-        p.poi.theta = theta; p.poi.court_poi = court_poi; p.poi.bstride = court_poi_bstride;
-        p.poi.N = N; p.poi.normalize = 1; p.poi.poi_out = poi_out;
-        p.poi.gt_poi = gt_poi; p.poi.nonzeros = nonzeros; p.poi.num_nonzero = num_nonzero;
-        p.poi.Rb = R_b; p.poi.K = dRb_dtheta;
+        if (a->N <= 0 || !a->poi_out) return SFH_E_BADARG;
+        if (a->gt_poi && (!a->nonzeros || !a->num_nonzero || !a->R_b || !a->dRb_dtheta)) return SFH_E_BADARG;
+        p.poi.theta = a->theta; p.poi.court_poi = a->court_poi; p.poi.bstride = a->court_poi_bstride;
+        p.poi.N = a->N; p.poi.normalize = 1; p.poi.poi_out = a->poi_out;
+        p.poi.gt_poi = a->gt_poi; p.poi.nonzeros = a->nonzeros; p.poi.num_nonzero = a->num_nonzero;
+        p.poi.Rb = a->R_b; p.poi.K = a->dRb_dtheta;
+        p.arrivals = p.ntiles + 1;
     }
+    p.weights = a->weights; p.w_f64 = a->weights_f64; p.w_outer = a->weights_outer;
+    p.rec_lambda = a->rec_lambda; p.reproj_lambda = a->reproj_lambda;
+    p.loss_out = a->loss_out; p.dtheta_total = a->dtheta_total;
     return launch_fused<SFH_MODE_BILINEAR, kEpiLoss>(p, poi_tail, (cudaStream_t)stream);
 }
 
-int sfh_predict_tail(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
-                     int mode, int nc, const float* logits, int h, int w, int B, int H, int W,
-                     int32_t* warp_out, float* score,
-                     const float* court_poi, int64_t court_poi_bstride, int N, float* poi_out,
-                     void* workspace, int64_t workspace_bytes, void* stream) {
+int sfh_predict_tail(const sfh_template* tmpl, const sfh_predict_tail_args* a, void* stream) {
     int rc = check_template(tmpl);
     if (rc) return rc;
-    if (!theta || !warp_out || B <= 0 || H <= 0 || W <= 0 || nc <= 0) return SFH_E_BADARG;
+    if (!a || !a->theta || !a->warp_out || a->B <= 0 || a->H <= 0 || a->W <= 0 || a->nc <= 0) return SFH_E_BADARG;
     if (tmpl->channels != 1) return SFH_E_BADARG;
-    if (score && (!logits || h <= 0 || w <= 0)) return SFH_E_BADARG;
+    if (a->score && (!a->logits || a->h <= 0 || a->w <= 0)) return SFH_E_BADARG;
     FusedParams p;
-    fill_common(p, theta, tmpl, xs, ys, B, H, W);
-    p.nc = nc; p.out_i = warp_out;
-    p.vec4 = (W % 4 == 0) && aligned16(warp_out);
-    if (score) {
-        if ((rc = setup_ws(p, workspace, workspace_bytes))) return rc;
-        p.logits = logits; p.lh = h; p.lw = w; p.score = score;
-        p.ratio = (h == H && w == W) ? 1 : (2 * h == H && 2 * w == W) ? 2 : 0;
+    fill_common(p, a->theta, tmpl, a->xs, a->ys, a->B, a->H, a->W);
+    p.nc = a->nc; p.out_i = a->warp_out;
+    p.vec4 = (a->W % 4 == 0) && aligned16(a->warp_out);
+    if (a->score) {
+        if ((rc = setup_ws(p, a->workspace, a->workspace_bytes))) return rc;
+        p.logits = a->logits; p.lh = a->h; p.lw = a->w; p.score = a->score;
+        p.ratio = (a->h == a->H && a->w == a->W) ? 1 : (2 * a->h == a->H && 2 * a->w == a->W) ? 2 : 0;
     }
-    const bool poi_tail = court_poi != nullptr;
+    const bool poi_tail = a->court_poi != nullptr;
     if (poi_tail) {
-        if (N <= 0 || !poi_out) return SFH_E_BADARG;
-        p.poi.theta = theta; p.poi.court_poi = court_poi; p.poi.bstride = court_poi_bstride;
-        p.poi.N = N; p.poi.normalize = 1; p.poi.poi_out = poi_out;
+        if (a->N <= 0 || !a->poi_out) return SFH_E_BADARG;
+        p.poi.theta = a->theta; p.poi.court_poi = a->court_poi; p.poi.bstride = a->court_poi_bstride;
+        p.poi.N = a->N; p.poi.normalize = 1; p.poi.poi_out = a->poi_out;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == SFH_MODE_NEAREST) rc = launch_fused<SFH_MODE_NEAREST, kEpiPredict>(p, poi_tail, st);
-    else if (mode == SFH_MODE_BILINEAR) rc = launch_fused<SFH_MODE_BILINEAR, kEpiPredict>(p, poi_tail, st);
+    if (a->mode == SFH_MODE_NEAREST) rc = launch_fused<SFH_MODE_NEAREST, kEpiPredict>(p, poi_tail, st);
+    else if (a->mode == SFH_MODE_BILINEAR) rc = launch_fused<SFH_MODE_BILINEAR, kEpiPredict>(p, poi_tail, st);
     else return SFH_E_BADMODE;
     if (rc) return rc;
-    if (score && p.ratio == 0) {
-        k_consistency_generic<<<B, kThreads, 0, st>>>(warp_out, logits, nc, H, W, h, w, score);
+    if (a->score && p.ratio == 0) {
+        k_consistency_generic<<<a->B, kThreads, 0, st>>>(a->warp_out, a->logits, a->nc, a->H, a->W, a->h, a->w, a->score);
         rc = (int)cudaGetLastError();
     }
     return rc;

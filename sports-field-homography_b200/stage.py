@@ -65,51 +65,71 @@ class _PoiFn(torch.autograd.Function):
 
 
 class _TrainTailFn(torch.autograd.Function):
-    """One launch: warp_mask, L_b (rec loss per sample), poi, R_b (reprojection per sample) and
-    the Jacobians J_b = dL_b/dtheta_b, K_b = dR_b/dtheta_b.  Backward is a scaled add."""
+    """One launch: warp_mask, L_b (rec loss per sample), poi, R_b (reprojection per sample), the
+    Jacobians J_b = dL_b/dtheta_b, K_b = dR_b/dtheta_b and — when weights are given — the
+    reference's weighted batch-mean loss with its dtheta.  Backward is a scaled add."""
 
     @staticmethod
-    def forward(ctx, theta9, stage, gt_masks, kind, want_mask, gt_poi, nonzeros, num_nonzero):
+    def forward(ctx, theta9, stage, gt_masks, kind, want_mask, gt_poi, nonzeros, num_nonzero,
+                weights, rec_lambda, reproj_lambda):
         B = theta9.shape[0]
         H, W = stage.height, stage.width
         dev = theta9.device
-        tmpl = stage.template
-        warp_out = torch.empty((B, H, W), dtype=torch.float32, device=dev) if want_mask else None
-        Lb = torch.empty(B, dtype=torch.float32, device=dev)
-        J = torch.empty((B, 9), dtype=torch.float32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
         with_poi = stage.court_poi is not None
         with_rep = with_poi and gt_poi is not None
+        with_loss = weights is not None
         N = stage.court_poi.shape[1] if with_poi else 0
-        poi = torch.empty((B, N, 2), dtype=torch.float32, device=dev) if with_poi else None
-        Rb = torch.empty(B, dtype=torch.float32, device=dev) if with_rep else None
-        K = torch.empty((B, 9), dtype=torch.float32, device=dev) if with_rep else None
+        warp_out = torch.empty((B, H, W), **f32) if want_mask else None
+        Lb, J = torch.empty(B, **f32), torch.empty((B, 9), **f32)
+        poi = torch.empty((B, N, 2), **f32) if with_poi else None
+        Rb = torch.empty(B, **f32) if with_rep else None
+        K = torch.empty((B, 9), **f32) if with_rep else None
+        loss = torch.empty((), **f32) if with_loss else None
+        dtot = torch.empty((B, 9), **f32) if with_loss else None
         xs, ys = stage.warper.grid_factors(dev)
         ws = _WS.get(dev, B, H, W)
-        d = tmpl.desc()
+        a = _lib.SfhTrainTailArgs()
+        a.theta, a.xs, a.ys, a.gt = theta9.data_ptr(), xs.data_ptr(), ys.data_ptr(), gt_masks.data_ptr()
+        a.B, a.H, a.W, a.nc, a.kind, a.N = B, H, W, stage.mask_classes, _lib.LOSS[kind], N
+        a.warp_out, a.L_b, a.dLb_dtheta = _ptr(warp_out), Lb.data_ptr(), J.data_ptr()
+        if with_poi:
+            a.court_poi, a.court_poi_bstride, a.poi_out = stage.court_poi.data_ptr(), stage.poi_bstride, poi.data_ptr()
+        if with_rep:
+            a.gt_poi, a.nonzeros, a.num_nonzero = gt_poi.data_ptr(), nonzeros.data_ptr(), num_nonzero.data_ptr()
+            a.R_b, a.dRb_dtheta = Rb.data_ptr(), K.data_ptr()
+        if with_loss:
+            a.weights = weights.data_ptr()
+            a.weights_f64 = int(weights.dtype == torch.float64)
+            a.weights_outer = int(weights.ndim == 2)
+            a.rec_lambda, a.reproj_lambda = float(rec_lambda), float(reproj_lambda)
+            a.loss_out, a.dtheta_total = loss.data_ptr(), dtot.data_ptr()
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        d = stage.template.desc()
         with torch.cuda.device(dev):
-            rc = _lib.lib().sfh_warp_loss_fwd_bwd(
-                theta9.data_ptr(), d, xs.data_ptr(), ys.data_ptr(), gt_masks.data_ptr(),
-                stage.mask_classes, _lib.LOSS[kind], B, H, W,
-                _ptr(warp_out), Lb.data_ptr(), J.data_ptr(),
-                _ptr(stage.court_poi) if with_poi else None, stage.poi_bstride, N,
-                _ptr(gt_poi) if with_rep else None, _ptr(nonzeros) if with_rep else None,
-                _ptr(num_nonzero) if with_rep else None,
-                _ptr(poi), _ptr(Rb), _ptr(K), ws.data_ptr(), ws.numel(), _stream())
+            rc = _lib.lib().sfh_warp_loss_fwd_bwd(d, a, _stream())
         _lib.check(rc, "sfh_warp_loss_fwd_bwd")
-        ctx.save_for_backward(theta9, J, K if with_rep else J)
-        ctx.with_rep, ctx.with_poi, ctx.stage = with_rep, with_poi, stage
+        ctx.save_for_backward(theta9, J, K if with_rep else J, dtot if with_loss else J)
+        ctx.with_rep, ctx.with_poi, ctx.with_loss, ctx.stage = with_rep, with_poi, with_loss, stage
         ctx.set_materialize_grads(False)       # unused outputs arrive as None: no zero-fill, no sync
-        outs = (warp_out if want_mask else Lb.new_empty(0), Lb,
-                poi if with_poi else Lb.new_empty(0), Rb if with_rep else Lb.new_empty(0))
+        e = Lb.new_empty(0)
+        outs = (warp_out if want_mask else e, Lb, poi if with_poi else e, Rb if with_rep else e,
+                loss if with_loss else e)
         ctx.mark_non_differentiable(outs[0])
         return outs
 
     @staticmethod
-    def backward(ctx, g_mask, g_Lb, g_poi, g_Rb):
-        theta9, J, K = ctx.saved_tensors
-        dth = torch.zeros_like(J) if g_Lb is None else g_Lb.reshape(-1, 1).to(torch.float32) * J
+    def backward(ctx, g_mask, g_Lb, g_poi, g_Rb, g_loss):
+        theta9, J, K, dtot = ctx.saved_tensors
+        dth = None
+        if g_Lb is not None:
+            dth = g_Lb.reshape(-1, 1).to(torch.float32) * J
         if ctx.with_rep and g_Rb is not None:
-            dth = dth + g_Rb.reshape(-1, 1).to(torch.float32) * K
+            t = g_Rb.reshape(-1, 1).to(torch.float32) * K
+            dth = t if dth is None else dth + t
+        if ctx.with_loss and g_loss is not None:
+            t = g_loss.to(torch.float32) * dtot
+            dth = t if dth is None else dth + t
         if ctx.with_poi and g_poi is not None:
             # poi was also used outside the fused reprojection loss: generic POI backward
             st = ctx.stage
@@ -119,8 +139,10 @@ class _TrainTailFn(torch.autograd.Function):
                 rc = _lib.lib().sfh_poi_bwd(theta9.data_ptr(), st.court_poi.data_ptr(), st.poi_bstride,
                                             g_poi.contiguous().data_ptr(), B, N, 1, extra.data_ptr(), _stream())
             _lib.check(rc, "sfh_poi_bwd")
-            dth = dth + extra
-        return dth, None, None, None, None, None, None, None
+            dth = extra if dth is None else dth + extra
+        if dth is None:
+            dth = torch.zeros_like(J)
+        return (dth,) + (None,) * 10
 
 
 class STNWarpStage(torch.nn.Module):
@@ -203,14 +225,18 @@ class STNWarpStage(torch.nn.Module):
         mask = torch.empty((B, H, W), dtype=torch.int32, device=self.device)
         xs, ys = self.warper.grid_factors(self.device)
         ws = _WS.get(self.device, B, H, W)
+        a = _lib.SfhPredictTailArgs()
+        a.theta, a.xs, a.ys = theta9.data_ptr(), xs.data_ptr(), ys.data_ptr()
+        a.B, a.H, a.W, a.mode, a.nc, a.h, a.w, a.N = B, H, W, _lib.MODE[self.mode], self.mask_classes, h, w, N
+        a.warp_out = mask.data_ptr()
+        if score is not None:
+            a.logits, a.score = logits.data_ptr(), score.data_ptr()
+        if want_poi:
+            a.court_poi, a.court_poi_bstride, a.poi_out = self.court_poi.data_ptr(), self.poi_bstride, poi.data_ptr()
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         d = self.template.desc()
         with torch.cuda.device(self.device):
-            rc = _lib.lib().sfh_predict_tail(
-                theta9.data_ptr(), d, xs.data_ptr(), ys.data_ptr(), _lib.MODE[self.mode],
-                self.mask_classes, _ptr(logits) if score is not None else None, h, w, B, H, W,
-                mask.data_ptr(), _ptr(score),
-                _ptr(self.court_poi) if want_poi else None, self.poi_bstride, N, _ptr(poi),
-                ws.data_ptr(), ws.numel(), _stream())
+            rc = _lib.lib().sfh_predict_tail(d, a, _stream())
         _lib.check(rc, "sfh_predict_tail")
         ret["warp_mask"] = mask
         if score is not None:
@@ -221,13 +247,20 @@ class STNWarpStage(torch.nn.Module):
 
     def train_tail(self, theta: torch.Tensor, gt_masks: torch.Tensor, rec_loss: str = "MSE",
                    gt_poi: Optional[torch.Tensor] = None, nonzeros: Optional[torch.Tensor] = None,
-                   num_nonzero: Optional[torch.Tensor] = None, want_mask: bool = True) -> dict:
+                   num_nonzero: Optional[torch.Tensor] = None, want_mask: bool = True,
+                   weights: Optional[torch.Tensor] = None, rec_lambda: float = 1.0,
+                   reproj_lambda: float = 1.0) -> dict:
         """Fused training tail.  Returns per-sample terms so the caller applies the reference's own
         weighting / reduction (models/losses.py:38-39 broadcasting quirk included):
 
             rec_per_sample    [B]  = mean_{h,w} crit(warp_mask, gt_masks/nc)     (train.py:195-196)
             reproj_per_sample [B]  = sum_n ||gt_poi-poi|| nonzeros / num_nonzero (models/losses.py:10-11)
             warp_mask [B,H,W] fp32 (no gradient flows through it on this path), poi [B,N,2]
+
+        With ``weights`` (the batch's ``gt_weights``: fp64 [B] or fp32 [B,1], train.py:159) the same
+        launch also returns the reference's scalar
+            loss = rec_lambda * mean(rec_per_sample * weights) + reproj_lambda * mean(reproj_per_sample)
+        (plain broadcasting, so [B,1] weights reproduce the [B,B] quirk) with d loss / d theta.
         """
         if self.mode != "bilinear":
             raise ValueError("train_tail needs a bilinear warper (nearest has no gradient)")
@@ -249,9 +282,20 @@ class STNWarpStage(torch.nn.Module):
             num_nonzero = _check_f32_cuda(num_nonzero, "num_nonzero", self.device)
             if tuple(gt_poi.shape) != (B, N, 2) or tuple(nonzeros.shape) != (B, N) or num_nonzero.numel() != B:
                 raise ValueError("gt_poi/nonzeros/num_nonzero shapes must be [B,N,2]/[B,N]/[B]")
-        mask, Lb, poi, Rb = _TrainTailFn.apply(theta9, self, gt_masks, rec_loss, want_mask,
-                                               gt_poi, nonzeros, num_nonzero)
+        if weights is not None:
+            if not isinstance(weights, torch.Tensor) or weights.device != self.device:
+                raise TypeError("weights must be a tensor on the stage's device")
+            if weights.dtype not in (torch.float32, torch.float64):
+                raise TypeError("weights must be float32 or float64")
+            if not (tuple(weights.shape) == (B,) or tuple(weights.shape) == (B, 1)):
+                raise ValueError(f"weights must be [B] or [B,1], got {tuple(weights.shape)}")
+            weights = weights.contiguous()
+        mask, Lb, poi, Rb, loss = _TrainTailFn.apply(theta9, self, gt_masks, rec_loss, want_mask,
+                                                     gt_poi, nonzeros, num_nonzero, weights,
+                                                     rec_lambda, reproj_lambda)
         ret = {"theta": theta, "rec_per_sample": Lb}
+        if weights is not None:
+            ret["loss"] = loss
         if want_mask:
             ret["warp_mask"] = mask
         if self.court_poi is not None:

@@ -28,3 +28,13 @@ def golden_real():
 def unpack2(bits, shape):
     b = np.unpackbits(bits)[: int(np.prod(shape)) * 2]
     return (b[0::2] * 2 + b[1::2]).reshape(shape).astype(np.int32)
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container (GPU tests run via gpurun)")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)

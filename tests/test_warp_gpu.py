@@ -1,0 +1,435 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI
+(libsfh_b200.so via ctypes), against
+  * the committed golden vectors produced by the reference's own code (tests/golden/),
+  * the plain-C op-order oracle and the torch restatement (on CPU and on the GPU itself —
+    the latter is what the reference really executes),
+at sizes up to BASELINE.json's full configs.
+
+Tolerances (BASELINE.json north_star):
+  warped float masks  <= 1e-5 abs         int / nearest masks  bit-exact
+  POI                 <= 1e-4 px          dtheta               <= 1e-4 relative (per-sample norm)
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import unpack2
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import sfh_b200
+    from sfh_b200 import synth
+    from oracle import c_oracle as co
+    from oracle import kornia_restated as kr
+    DEV = torch.device("cuda:0")
+
+TOL_MASK = 1e-5
+TOL_POI_PX = 1e-4
+TOL_GRAD = 1e-4
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+def relnorm(a, b):
+    a = np.asarray(a, np.float64).reshape(a.shape[0], -1)
+    b = np.asarray(b, np.float64).reshape(b.shape[0], -1)
+    return np.linalg.norm(a - b, axis=1) / (np.linalg.norm(b, axis=1) + 1e-300)
+
+
+def test_native_library_is_loaded():
+    l = sfh_b200._lib.lib()
+    assert l.sfh_abi_version() == 1
+    assert b"sm_100a" in l.sfh_build_info()
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+# ------------------------------------------------------------------------------ golden vectors
+def test_golden_small_all_outputs(golden_small):
+    g = golden_small
+    B = g["theta"].shape[0]
+    H, W = g["template"].shape
+    tmpl = cu(g["template"])[None, None].repeat(B, 1, 1, 1)
+    poi = cu(g["court_poi"])[None].repeat(B, 1, 1)
+    th = cu(g["theta"])
+    for nearest, key in ((False, "warp_bilinear"), (True, "warp_nearest")):
+        st = sfh_b200.STNWarpStage(tmpl, poi, (W, H), 4, warp_with_nearest=nearest)
+        out = st.warp(th).cpu().numpy()
+        assert out.shape == (B, H, W)
+        if nearest:
+            assert np.array_equal(out, g[key])
+        else:
+            assert np.abs(out - g[key]).max() <= TOL_MASK
+    st = sfh_b200.STNWarpStage(tmpl, poi, (W, H), 4)
+    p = st.transform_poi(th).cpu().numpy()
+    assert np.abs(p - g["poi"]).max() * W <= 2e-3 * 1   # vs reference fp32 LU (its own noise); see fp64 test
+    # predict tail through the fused launch
+    for tag in ("half", "full", "odd"):
+        for mode in ("nearest", "bilinear"):
+            stp = sfh_b200.STNWarpStage(tmpl, poi, (W, H), 4, warp_with_nearest=(mode == "nearest"))
+            r = stp.predict_tail(th, cu(g[f"pred_{tag}_logits"]), consistency=True, project_poi=True)
+            assert r["warp_mask"].dtype == torch.int32 and r["consist_score"].dtype == torch.float32
+            m = r["warp_mask"].cpu().numpy()
+            ref = g[f"pred_{tag}_{mode}_mask"]
+            if mode == "nearest":
+                assert np.array_equal(m, ref), (tag, mode)
+            else:
+                assert (m != ref).mean() < 1e-3
+            np.testing.assert_allclose(r["consist_score"].cpu().numpy(), g[f"pred_{tag}_{mode}_score"],
+                                       rtol=1e-5 if mode == "nearest" else 2e-3)
+            assert np.abs(r["poi"].cpu().numpy() - g[f"pred_{tag}_{mode}_poi"]).max() * W <= 2e-3
+
+
+def test_golden_small_losses_and_gradients(golden_small):
+    g = golden_small
+    B = g["theta"].shape[0]
+    H, W = g["template"].shape
+    tmpl = cu(g["template"])[None, None].repeat(B, 1, 1, 1)
+    poi = cu(g["court_poi"])[None].repeat(B, 1, 1)
+    st = sfh_b200.STNWarpStage(tmpl, poi, (W, H), 4)
+    gt = cu(g["gt"])
+    for kind, name in (("MSE", "mse"), ("SmoothL1", "sl1")):
+        for wn in ("w1", "w2"):
+            th = cu(g["theta"]).requires_grad_(True)
+            r = st.train_tail(th, gt, kind, cu(g["gt_poi"]), cu(g["nonzeros"]), cu(g["num_nonzero"]))
+            np.testing.assert_allclose(r["rec_per_sample"].detach().cpu().numpy(), g[f"rec_{name}_per_sample"], rtol=1e-5)
+            loss = sfh_b200.weight_and_reduce(r["rec_per_sample"], cu(g[wn]))   # models/losses.py:38-39
+            np.testing.assert_allclose(loss.item(), g[f"rec_{name}_{wn}"], rtol=1e-5)
+            loss.backward()
+            err = relnorm(th.grad.cpu().numpy(), g[f"rec_{name}_{wn}_dtheta"])
+            assert err.max() <= TOL_GRAD, (kind, wn, err)
+            assert np.abs(r["warp_mask"].cpu().numpy() - g["warp_bilinear"]).max() <= TOL_MASK
+    # weighting + lambdas + batch means inside the launch (train.py:196,213; models/losses.py:38-39),
+    # for both weight shapes ([B] fp64 elementwise, [B,1] fp32 -> the [B,B] broadcast quirk)
+    for kind, name in (("MSE", "mse"), ("SmoothL1", "sl1")):
+        for wn in ("w1", "w2"):
+            th = cu(g["theta"]).requires_grad_(True)
+            r = st.train_tail(th, gt, kind, cu(g["gt_poi"]), cu(g["nonzeros"]), cu(g["num_nonzero"]),
+                              weights=cu(g[wn]), rec_lambda=2.0, reproj_lambda=8.0)
+            expect = 2.0 * g[f"rec_{name}_{wn}"] + 8.0 * g["reproj_mean"]
+            np.testing.assert_allclose(r["loss"].item(), expect, rtol=2e-5)
+            r["loss"].backward()
+            ref = 2.0 * g[f"rec_{name}_{wn}_dtheta"] + 8.0 * g["reproj_mean_dtheta"]
+            err = relnorm(th.grad.cpu().numpy(), ref)
+            assert err.max() <= 2e-3, (kind, wn, err)      # reproj part vs the reference's fp32 LU inverse
+            r = st.train_tail(cu(g["theta"]), gt, kind, weights=cu(g[wn]), rec_lambda=3.0, want_mask=False)
+            np.testing.assert_allclose(r["loss"].item(), 3.0 * g[f"rec_{name}_{wn}"], rtol=1e-5)
+    # reprojection loss through the fused tail and through the stand-alone op
+    for red in ("mean", "sum"):
+        th = cu(g["theta"]).requires_grad_(True)
+        r = st.train_tail(th, gt, "MSE", cu(g["gt_poi"]), cu(g["nonzeros"]), cu(g["num_nonzero"]))
+        loss = r["reproj_per_sample"].mean() if red == "mean" else r["reproj_per_sample"].sum()
+        np.testing.assert_allclose(loss.item(), g[f"reproj_{red}"], rtol=2e-5)
+        loss.backward()
+        err = relnorm(th.grad.cpu().numpy(), g[f"reproj_{red}_dtheta"])
+        assert err.max() <= 2e-3, err      # reference gradient goes through an fp32 LU inverse
+        th2 = cu(g["theta"]).requires_grad_(True)
+        p = st.transform_poi(th2)
+        l2 = sfh_b200.reprojection_loss(p, cu(g["gt_poi"]), cu(g["nonzeros"]), cu(g["num_nonzero"]), red)
+        np.testing.assert_allclose(l2.item(), g[f"reproj_{red}"], rtol=2e-5)
+        l2.backward()
+        assert relnorm(th2.grad.cpu().numpy(), g[f"reproj_{red}_dtheta"]).max() <= 2e-3
+    pin = cu(g["poi"]).requires_grad_(True)
+    sfh_b200.reprojection_loss(pin, cu(g["gt_poi"]), cu(g["nonzeros"]), cu(g["num_nonzero"])).backward()
+    np.testing.assert_allclose(pin.grad.cpu().numpy(), g["reproj_mean_dpoi"], rtol=1e-4, atol=1e-7)
+    # drop-in autograd: arbitrary upstream gradients through warp() and transform_poi()
+    th = cu(g["theta"]).requires_grad_(True)
+    st.warp(th).backward(cu(g["warp_grad_out"]))
+    assert relnorm(th.grad.cpu().numpy(), g["warp_dtheta"]).max() <= TOL_GRAD
+    th = cu(g["theta"]).requires_grad_(True)
+    st.transform_poi(th).backward(cu(g["poi_grad_out"]))
+    assert relnorm(th.grad.cpu().numpy(), g["poi_dtheta"]).max() <= 2e-3
+
+
+def test_golden_real_thetas(golden_real):
+    g = golden_real
+    th = cu(g["theta"])
+    for (W, H) in [(640, 360), (1280, 720)]:
+        tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (W, H), 4, 2)
+        tmpl, poi = tmpl.to(DEV), poi.to(DEV)
+        r = sfh_b200.STNWarpStage(tmpl, poi, (W, H), 4, warp_with_nearest=True).predict_tail(th, None, False, True)
+        assert np.array_equal(r["warp_mask"].cpu().numpy(), unpack2(g[f"nearest_{W}x{H}_bits"], (2, H, W)))
+        wb = sfh_b200.STNWarpStage(tmpl, poi, (W, H), 4).warp(th).cpu().numpy()
+        assert np.abs(wb[:, ::7, ::5] - g[f"bilinear_{W}x{H}_sample"]).max() <= TOL_MASK
+        np.testing.assert_allclose(wb.astype(np.float64).sum((1, 2)), g[f"bilinear_{W}x{H}_sum"], rtol=1e-6)
+        p64 = co.poi_fwd(g["theta"], poi.cpu().numpy())
+        assert np.abs(r["poi"].cpu().numpy() - p64).max() * W <= TOL_POI_PX
+
+
+# ------------------------------------------------------------------- oracle parity, all formats
+CASES = [
+    # W, H, B, family, scale
+    (640, 360, 16, "a", 1.0),      # C1
+    (640, 360, 8, "b", 1.0),
+    (1280, 720, 4, "a", 1.0),      # C3/C4 size
+    (1280, 720, 3, "b", 1.0),
+    (200, 77, 5, "a", 1.0),        # ragged: W % 128 != 0, H % 16 != 0
+    (130, 50, 3, "a", 7.0),        # W % 4 != 0 (scalar stores)
+]
+
+
+def _thetas(fam, B, seed):
+    return synth.theta_family_a(B, seed) if fam == "a" else synth.theta_family_b(B, seed)
+
+
+@pytest.mark.parametrize("W,H,B,fam,scale", CASES)
+@pytest.mark.parametrize("mode", ["bilinear", "nearest"])
+def test_warp_forward_matches_oracles(W, H, B, fam, scale, mode):
+    name = "ncaa_nc4"
+    size = (1280, 720) if W > 640 else (640, 360)
+    tmpl, _ = sfh_b200.load_bundled(name, size, 4, 1)
+    th = _thetas(fam, B, 100 + W) * scale
+    ref_c = co.warp_fwd(th.numpy(), tmpl.numpy(), H, W, mode)[:, 0]
+    d_t = tmpl.to(DEV)
+    packed = sfh_b200.STNWarpStage(d_t, None, (W, H), 4, warp_with_nearest=(mode == "nearest"))
+    assert packed.template.fmt == sfh_b200._lib.TMPL_Q2
+    out_q = packed.warp(th.to(DEV)).cpu().numpy()
+    wf = sfh_b200.HomographyWarper(H, W, mode=mode)
+    out_f = wf(d_t.expand(B, -1, -1, -1), th.to(DEV))[:, 0].cpu().numpy()      # plain fp32 template path
+    # reference executed on this GPU by stock ATen (what the reference really runs)
+    ref_g = kr.HomographyWarper(H, W, mode=mode)(d_t.expand(B, -1, -1, -1), th.to(DEV))[:, 0].cpu().numpy()
+    assert np.array_equal(out_q, out_f)            # template format must not change a single bit
+    if mode == "nearest":
+        # bit-exact vs the oracle except flips on exact rounding ties of the sampling coordinate
+        for ref in (ref_c, ref_g):
+            assert (out_q != ref).mean() <= 2e-6, (out_q != ref).mean()
+    else:
+        bad_c = np.abs(out_q - ref_c) > TOL_MASK
+        bad_g = np.abs(out_q - ref_g) > TOL_MASK
+        # the kernel replays ATen's op order: it must agree with ATen-on-GPU within tolerance
+        # everywhere; vs the CPU oracle only meshgrid-division rounding may differ (edge pixels)
+        assert bad_g.mean() == 0.0, (bad_g.mean(), np.abs(out_q - ref_g).max())
+        assert bad_c.mean() <= 5e-3, bad_c.mean()
+
+
+def test_q4_palette_and_float_templates():
+    """8-class template (Q4), arbitrary float template (F32, C=3, per-sample)."""
+    rng = np.random.default_rng(0)
+    W, H, B = 256, 144, 4
+    cls = rng.integers(0, 8, size=(36, 64)).repeat(4, 0).repeat(4, 1)
+    tmpl = torch.from_numpy((cls / 8.0).astype(np.float32))[None, None]
+    th = synth.theta_family_a(B, 3)
+    st = sfh_b200.STNWarpStage(tmpl.to(DEV), None, (W, H), 8)
+    assert st.template.fmt == sfh_b200._lib.TMPL_Q4
+    ref = co.warp_fwd(th.numpy(), tmpl.numpy(), H, W)[:, 0]
+    assert np.abs(st.warp(th.to(DEV)).cpu().numpy() - ref).max() <= TOL_MASK
+    t7 = torch.from_numpy((rng.integers(0, 7, size=(40, 60)) / 7.0).astype(np.float32))[None, None]
+    st7 = sfh_b200.STNWarpStage(t7.to(DEV), None, (W, H), 7)
+    ref7 = co.warp_fwd(th.numpy(), t7.numpy(), H, W)[:, 0]
+    assert np.abs(st7.warp(th.to(DEV)).cpu().numpy() - ref7).max() <= TOL_MASK
+    ft = torch.from_numpy(rng.random((B, 3, 45, 80), dtype=np.float32))
+    out = sfh_b200.HomographyWarper(H, W)(ft.to(DEV), th.to(DEV)).cpu().numpy()
+    assert np.abs(out - co.warp_fwd(th.numpy(), ft.numpy(), H, W)).max() <= TOL_MASK
+    outn = sfh_b200.HomographyWarper(H, W, mode="nearest")(ft.to(DEV), th.to(DEV)).cpu().numpy()
+    assert (outn != co.warp_fwd(th.numpy(), ft.numpy(), H, W, "nearest")).mean() < 1e-5
+    # backward through a multi-channel float template
+    thg = th.to(DEV).requires_grad_(True)
+    o = sfh_b200.HomographyWarper(H, W)(ft.to(DEV), thg)
+    go = torch.randn(o.shape, generator=torch.Generator().manual_seed(1))
+    o.backward(go.to(DEV))
+    ref = co.warp_bwd(th.numpy(), ft.numpy(), go.numpy())
+    assert relnorm(thg.grad.cpu().numpy().reshape(B, 3, 3), ref).max() <= TOL_GRAD
+
+
+@pytest.mark.parametrize("W,H,B,fam", [(640, 360, 64, "a"), (640, 360, 16, "b"), (1280, 720, 4, "a"), (200, 77, 5, "a")])
+@pytest.mark.parametrize("kind", ["MSE", "SmoothL1"])
+def test_fused_train_tail_matches_oracle(W, H, B, fam, kind):
+    """C2: warp + rec loss + reprojection RMSE + dL/dtheta in one launch, full BASELINE size."""
+    size = (1280, 720) if W > 640 else (640, 360)
+    tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", size, 4, 1)
+    th = _thetas(fam, B, 7)
+    gt = (co.warp_fwd(synth.perturb(th).numpy(), tmpl.numpy(), H, W, "nearest")[:, 0] * 4).astype(np.int64)
+    warp_ref, Lb_ref, J_ref = co.warp_loss(th.numpy(), tmpl.numpy(), gt, 4, kind)
+    gt_poi = co.poi_fwd(synth.perturb(th, seed=5).numpy(), poi.expand(B, -1, -1).numpy())
+    rng = np.random.default_rng(1)
+    nz = (rng.random((B, poi.shape[1])) < 0.8).astype(np.float32)
+    nz[:, 0] = 1
+    num = nz.sum(1)
+    st = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (W, H), 4)
+    thg = th.to(DEV).requires_grad_(True)
+    r = st.train_tail(thg, cu(gt), kind, cu(gt_poi), cu(nz), cu(num))
+    assert np.abs(r["warp_mask"].cpu().numpy() - warp_ref).max() <= TOL_MASK
+    np.testing.assert_allclose(r["rec_per_sample"].detach().cpu().numpy(), Lb_ref, rtol=1e-5)
+    w = torch.rand(B, generator=torch.Generator().manual_seed(2)) + 0.5
+    (r["rec_per_sample"] * w.to(DEV)).mean().backward()
+    ref = J_ref * (w.numpy() / B)[:, None, None]
+    err = relnorm(thg.grad.cpu().numpy().reshape(B, 3, 3), ref)
+    assert err.max() <= TOL_GRAD, err
+    # POI / reprojection against the fp64 oracle
+    p64 = co.poi_fwd(th.numpy(), poi.expand(B, -1, -1).numpy())
+    assert np.abs(r["poi"].detach().cpu().numpy() - p64).max() * W <= TOL_POI_PX
+    Rb = co.reproj_per_sample(p64, gt_poi, nz, num)
+    np.testing.assert_allclose(r["reproj_per_sample"].detach().cpu().numpy(), Rb, rtol=1e-5)
+    # the same loss without materialising the mask must give the same numbers
+    r2 = st.train_tail(th.to(DEV), cu(gt), kind, want_mask=False)
+    assert torch.equal(r2["rec_per_sample"], r["rec_per_sample"].detach())
+    # ... and the unfused drop-in path (warp -> torch loss -> autograd) the same gradient
+    th3 = th.to(DEV).requires_grad_(True)
+    l3 = kr.rec_loss_per_sample(st.warp(th3), cu(gt), 4, kind)
+    (l3 * w.to(DEV)).mean().backward()
+    assert relnorm(th3.grad.cpu().numpy().reshape(B, 3, 3), ref).max() <= TOL_GRAD
+
+
+def test_reprojection_gradient_matches_fp64_autograd():
+    B = 8
+    _, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, B)
+    th = synth.theta_family_b(B, 3)
+    gt_poi = kr.transform_poi(synth.perturb(th, seed=1).double(), poi.double())
+    nz = (torch.rand(B, poi.shape[1], generator=torch.Generator().manual_seed(4)) < 0.8).double()
+    nz[:, 0] = 1
+    num = nz.sum(1)
+    t64 = th.double().requires_grad_(True)
+    l64 = kr.reprojection_loss(kr.transform_poi(t64, poi.double()), gt_poi, nz, num, "sum")
+    l64.backward()
+    tmpl, _ = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 1)
+    st = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (640, 360), 4)
+    tg = th.to(DEV).requires_grad_(True)
+    p = st.transform_poi(tg)
+    l = sfh_b200.reprojection_loss(p, gt_poi.float().to(DEV), nz.float().to(DEV), num.float().to(DEV), "sum")
+    l.backward()
+    np.testing.assert_allclose(l.item(), l64.item(), rtol=1e-5)
+    assert relnorm(tg.grad.cpu().numpy(), t64.grad.numpy()).max() <= TOL_GRAD
+    assert np.abs(p.detach().cpu().numpy() - kr.transform_poi(th.double(), poi.double()).numpy()).max() * 1280 <= TOL_POI_PX
+
+
+@pytest.mark.parametrize("W,H,B,name", [(1280, 720, 15, "ncaa_nc4"), (1280, 720, 8, "pitch_v3_nc4"), (640, 360, 6, "ncaa_nc4")])
+def test_predict_tail_matches_oracle(W, H, B, name):
+    """C3/C4: int32 mask + CE consistency vs logits [B,4,360,640] + POI, one launch."""
+    tmpl, poi = sfh_b200.load_bundled(name, (W, H), 4, 1)
+    th = synth.theta_family_b(B, 21)
+    lh, lw = 360, 640
+    logits = torch.randn(B, 4, lh, lw, generator=torch.Generator().manual_seed(8))
+    m_ref, s_ref = co.predict_tail(th.numpy(), tmpl.numpy(), logits.numpy(), 4, H, W, "nearest")
+    st = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, warp_with_nearest=True)
+    r = st.predict_tail(th.to(DEV), logits.to(DEV), consistency=True, project_poi=True)
+    m = r["warp_mask"].cpu().numpy()
+    flips = (m != m_ref).mean()
+    assert flips <= 2e-6, flips
+    np.testing.assert_allclose(r["consist_score"].cpu().numpy(), s_ref, rtol=1e-5)
+    p64 = co.poi_fwd(th.numpy(), poi.expand(B, -1, -1).numpy())
+    assert np.abs(r["poi"].cpu().numpy() - p64).max() * W <= TOL_POI_PX
+    # without consistency / poi the dict shrinks exactly like the reference's
+    r2 = st.predict_tail(th.to(DEV), None, consistency=False, project_poi=False)
+    assert set(r2) == {"theta", "warp_mask"} and torch.equal(r2["warp_mask"], r["warp_mask"])
+
+
+def test_transform_points_matches_kornia_restatement():
+    B, N = 5, 52
+    g = torch.Generator().manual_seed(0)
+    pts = torch.rand(B, N, 2, generator=g) * 2 - 1
+    T = synth.theta_family_a(B, 9)
+    for tr in (T, T[:, 0], T[:1, 0]):
+        ref = kr.transform_points(tr, pts)
+        out = sfh_b200.transform_points(tr.to(DEV), pts.to(DEV))
+        assert out.shape == ref.shape
+        assert np.abs(out.cpu().numpy() - ref.numpy()).max() <= 1e-6
+    trg = T[:, 0].to(DEV).requires_grad_(True)
+    pg = pts.to(DEV).requires_grad_(True)
+    go = torch.randn(B, N, 2, generator=g)
+    sfh_b200.transform_points(trg, pg).backward(go.to(DEV))
+    t64 = T[:, 0].double().requires_grad_(True)
+    p64 = pts.double().requires_grad_(True)
+    kr.transform_points(t64, p64).backward(go.double())
+    assert relnorm(trg.grad.cpu().numpy(), t64.grad.numpy()).max() <= TOL_GRAD
+    np.testing.assert_allclose(pg.grad.cpu().numpy(), p64.grad.numpy(), rtol=1e-4, atol=1e-6)
+
+
+# ----------------------------------------------------------------- size-independent properties
+def test_properties_at_full_size():
+    W, H, B = 1280, 720, 32
+    tmpl, poi = sfh_b200.load_bundled("pitch_v3_nc4", (W, H), 4, 1)      # C4
+    th = synth.theta_family_b(B, 77).to(DEV)
+    stn = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, warp_with_nearest=True)
+    stb = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (W, H), 4)
+    a = stn.predict_tail(th, None, False, True)
+    b = stn.predict_tail(th, None, False, True)
+    assert torch.equal(a["warp_mask"], b["warp_mask"]) and torch.equal(a["poi"], b["poi"])   # deterministic
+    # int32 mask == nearest float mask * nc, classes stay in range
+    f = stn.warp(th)
+    assert torch.equal((f * 4).to(torch.int32), a["warp_mask"])
+    assert int(a["warp_mask"].min()) >= 0 and int(a["warp_mask"].max()) <= 3
+    # batch sharding does not change any sample (no cross-sample state)
+    lo = stn.predict_tail(th[:13], None, False, False)["warp_mask"]
+    hi = stn.predict_tail(th[13:], None, False, False)["warp_mask"]
+    assert torch.equal(torch.cat([lo, hi]), a["warp_mask"])
+    # bilinear output is a convex combination of template values
+    wb = stb.warp(th)
+    assert float(wb.min()) >= 0.0 and float(wb.max()) <= 0.75 + 1e-6
+    # gradient of a loss that does not depend on theta-sensitive pixels: nearest => exactly zero
+    t2 = th.clone().requires_grad_(True)
+    stn.warp(t2).sum().backward()
+    assert float(t2.grad.abs().max()) == 0.0
+    # fused reductions are deterministic run to run (fixed-order, no data atomics)
+    gt = a["warp_mask"].to(torch.int64)
+    r1 = stb.train_tail(th, gt, "MSE", want_mask=False)["rec_per_sample"]
+    r2 = stb.train_tail(th, gt, "MSE", want_mask=False)["rec_per_sample"]
+    assert torch.equal(r1, r2)
+
+
+def test_nonfinite_and_degenerate_theta():
+    W, H = 640, 360
+    tmpl, _ = sfh_b200.load_bundled("ncaa_nc4", (W, H), 4, 1)
+    th = torch.eye(3)[None, None].repeat(4, 1, 1, 1)
+    th[0, 0, 0, 0] = float("nan")           # non-finite -> all zeros (ATen CUDA rule)
+    th[1, 0, 0, 2] = 5.0                    # fully out of bounds -> zeros
+    th[2, 0, 2, 2] = 1e-9                   # |z| <= eps -> scale = 1
+    th[2, 0, 2, 0] = 0.0
+    th[3, 0] *= 1e30                        # huge but finite
+    st = sfh_b200.STNWarpStage(tmpl.to(DEV), None, (W, H), 4)
+    out = st.warp(th.to(DEV)).cpu().numpy()
+    ref = co.warp_fwd(th.numpy(), tmpl.numpy(), H, W)[:, 0]
+    assert float(np.abs(out[0]).max()) == 0.0 and float(np.abs(out[1]).max()) == 0.0
+    assert np.abs(out - ref).max() <= TOL_MASK
+
+
+# ---------------------------------------------------------------------- API / error conventions
+def test_error_conventions_and_state_dict():
+    tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 2)
+    st = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (640, 360), 4)
+    assert len(st.state_dict()) == 0                       # court_img / court_poi are plain attributes
+    with pytest.raises(TypeError):
+        st.warp(torch.eye(3)[None])                        # CPU theta: no CPU path
+    with pytest.raises(TypeError):
+        st.warp(torch.eye(3, dtype=torch.float64)[None].to(DEV))
+    with pytest.raises(ValueError):
+        st.warp(torch.zeros(2, 2, 3, device=DEV))
+    with pytest.raises(TypeError):
+        st.train_tail(torch.eye(3)[None].to(DEV), torch.zeros(1, 360, 640, dtype=torch.int32, device=DEV))
+    with pytest.raises(ValueError):
+        st.train_tail(torch.eye(3)[None].to(DEV), torch.zeros(1, 36, 64, dtype=torch.int64, device=DEV))
+    th = torch.eye(3)[None, None].to(DEV)
+    assert torch.equal(st.warp(th), st.warp(th[:, 0]))     # [B,1,3,3] and [B,3,3] both accepted
+    w = sfh_b200.HomographyWarper(360, 640)
+    with pytest.raises(TypeError):
+        w(tmpl, th)                                        # patch on CPU, theta on GPU
+
+
+class _FakeNet(torch.nn.Module):
+    """The attributes patch_reconstructor touches on a reference Reconstructor."""
+
+    def __init__(self, court_img, court_poi, size, nearest):
+        super().__init__()
+        self.court_img, self.court_poi = court_img, court_poi
+        self.mask_classes, self.use_unet, self.use_resnet = 4, False, False
+        self.warper = kr.HomographyWarper(size[1], size[0], mode="nearest" if nearest else "bilinear")
+        self.reg = torch.nn.Linear(2, 2)
+
+
+def test_patch_reconstructor_keeps_signatures_and_state_dict():
+    tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 4)
+    net = _FakeNet(tmpl.to(DEV), poi.to(DEV), (640, 360), False).to(DEV)
+    keys = set(net.state_dict())
+    sfh_b200.patch_reconstructor(net)
+    assert set(net.state_dict()) == keys
+    th = synth.theta_family_a(3, 5).to(DEV)
+    out = net.warp(th, net.court_img)                      # reference call shape (:191)
+    assert out.shape == (3, 360, 640)
+    ref = kr.warp(th, net.court_img, 360, 640)
+    assert float((out - ref).abs().max()) <= TOL_MASK
+    p = net.transform_poi(th, net.court_poi)               # (:186)
+    assert p.shape == (3, 52, 2)
