@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the STN warp stage (BASELINE.json metric: warped frames/s, fwd+bwd).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+A "step" is one pass of the hot path over one batch of synthetic input (random homographies
+injected at the warp boundary, real court template).  Default workload `c2` is
+BASELINE.json configs[1]: training warp fwd+bwd at 640x360, batch 64 per GPU — warp_mask +
+MSE loss vs int64 gt + POI reprojection RMSE + weighted batch-mean loss and dL/dtheta, ONE
+kernel launch per step.  Work is batch-sharded: every rank processes its own 64 frames (weak
+scaling); the only exchange is one all-reduce of the loss numerators per step.
+
+value     whole-job frames/s with inputs resident in HBM (steps replayed from CUDA graphs so the
+          Python launch cost does not gate a ~35 us kernel); buffers rotate through > 4x L2.
+e2e       same metric through the public API with HOST (pinned) inputs: H2D of the step's inputs
+          and D2H of loss + dtheta inside the timed region.
+roofline  algorithmic bytes per launch / mean kernel duration (per-launch CUDA-event pairs on the
+          launching stream) vs MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline  the restated kornia path (oracle/, torch CPU, all host threads) on a bounded sample.
+--impl reference   the same CPU path as its own arm (the reference is pure Python + kornia; kornia
+          is not installable offline, so the arm runs the oracle port of it — DESIGN.md).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (W, H, B per GPU, template, kind, description, algorithmic bytes per frame)
+    "c2": (640, 360, 64, "ncaa_nc4", "train",
+           "C2 training warp fwd+bwd 640x360 batch 64/GPU: warp_mask fp32 + MSE vs int64 gt + POI RRMSE + dL/dtheta (NCAA v4 nc4 template, theta family A)",
+           640 * 360 * 12),
+    "c2hd": (1280, 720, 64, "ncaa_nc4", "train",
+             "training warp fwd+bwd 1280x720 batch 64/GPU (same work as C2 at HD)", 1280 * 720 * 12),
+    "c1": (640, 360, 16, "ncaa_nc4", "fwd",
+           "C1 bilinear forward 640x360 batch 16, fp32 mask out", 640 * 360 * 4),
+    "c3": (1280, 720, 15, "ncaa_nc4", "predict",
+           "C3 predict tail 1280x720 batch 15: nearest warp -> int32 mask + CE consistency vs logits [4,360,640] + POI",
+           1280 * 720 * 4 + 4 * 360 * 640 * 4),
+    "c4": (1280, 720, 32, "pitch_v3_nc4", "fwd",
+           "C4 pitch v3 HD template bilinear forward 1280x720 batch 32 + POI", 1280 * 720 * 4),
+}
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads / cpu baseline")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.stop, self.thread, self.h = [], threading.Event(), None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def finish(self, t0, t1):
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop.set()
+        self.thread.join()
+        nv = self.nv
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "sw_power_cap": 0x4, "hw_power_brake": 0x80, "sync_boost": 0x10}
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        return {"sm_mhz": statistics.median([s[1] for s in inside]) if inside else None,
+                "sm_max_mhz": mx, "samples": len(inside),
+                "reasons": [k for k, v in names.items() if bits & v]}
+
+
+# ------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_step(W, H, B, kind, tmpl, poi, seed=0):
+    """The reference's CPU path for one batch (restated kornia ops on torch CPU, autograd backward).
+    Returns a callable running one step on B frames."""
+    import torch
+    from oracle import kornia_restated as kr
+    from sfh_b200 import synth
+    th0 = synth.theta_family_a(B, 1234 + seed)
+    tm = tmpl.expand(B, -1, -1, -1).contiguous()
+    pp = poi.expand(B, -1, -1).contiguous()
+    with torch.no_grad():
+        gt = (kr.warp(synth.perturb(th0), tm, H, W, "nearest") * 4).to(torch.int64)
+        gt_poi = kr.transform_poi(synth.perturb(th0, seed=5), pp)
+    nz = torch.ones(B, pp.shape[1])
+    num = nz.sum(1)
+    w = torch.ones(B, dtype=torch.float64)
+    logits = torch.randn(B, 4, 360, 640, generator=torch.Generator().manual_seed(3)) if kind == "predict" else None
+
+    def step():
+        if kind == "train":
+            th = th0.clone().requires_grad_(True)
+            warp = kr.warp(th, tm, H, W, "bilinear")
+            p = kr.transform_poi(th, pp)
+            loss = kr.per_sample_weighted_criterion(torch.nn.MSELoss(reduction="none"), warp,
+                                                    gt.to(torch.float32) / 4.0, w) \
+                + 8.0 * kr.reprojection_loss(p, gt_poi, nz, num)
+            loss.backward()
+            return float(loss.detach())
+        with torch.no_grad():
+            if kind == "fwd":
+                return float(kr.warp(th0, tm, H, W, "bilinear").sum()) + float(kr.transform_poi(th0, pp).sum())
+            r = kr.predict_tail(th0, tm, logits, pp, 4, H, W, "nearest")
+            return float(r["consist_score"].sum())
+    return step
+
+
+def run_cpu(workload, steps, warmup, sample_frames=16, budget_s=None):
+    import torch
+    import sfh_b200
+    W, H, B, name, kind, desc, _ = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tmpl, poi = sfh_b200.load_bundled(name, (W, H), 4, 1)
+    Bs = min(B, sample_frames)
+    if budget_s is not None:       # size the per-step sample so steps+warmup fit the time budget
+        probe = cpu_reference_step(W, H, 4, kind, tmpl, poi)
+        probe()
+        t0 = time.perf_counter()
+        probe()
+        per_frame = (time.perf_counter() - t0) / 4
+        Bs = int(max(1, min(B, budget_s / ((steps + warmup) * per_frame))))
+    step = cpu_reference_step(W, H, Bs, kind, tmpl, poi)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": Bs / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} steps x {Bs} frames of workload {workload} ({W}x{H}, {kind}), "
+                      f"oracle/kornia_restated.py on torch CPU with {cores} threads, {dt * 1e3:.1f} ms/step",
+            "ms_per_step": dt * 1e3, "frames_per_step": Bs}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    W, H, B, name, kind, desc, bpf = WORKLOADS[args.workload]
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    r = run_cpu(args.workload, steps, warm, budget_s=120.0)
+    line = {"impl": "reference", "metric": "warped frames/s (fwd+bwd)", "value": r["value"], "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "frames_per_step": r["frames_per_step"], "device": "host CPU",
+                       "note": "reference = kornia path restated on torch CPU ops (kornia itself is not installable offline); "
+                               "each step is a bounded sample of the batch sized so steps+warmup end within ~2 minutes"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+class Workload:
+    """Device-resident rotating buffer sets + the public-API call of one step."""
+
+    def __init__(self, name, dev, seed):
+        import torch
+        import sfh_b200
+        from sfh_b200 import synth
+        self.torch = torch
+        self.W, self.H, self.B, tname, self.kind, self.desc, self.bytes_per_frame = WORKLOADS[name]
+        W, H, B = self.W, self.H, self.B
+        tmpl, poi = sfh_b200.load_bundled(tname, (W, H), 4, 1)
+        self.tmpl_cpu, self.poi_cpu = tmpl, poi
+        self.stage = sfh_b200.STNWarpStage(tmpl.to(dev), poi.to(dev), (W, H), 4,
+                                           warp_with_nearest=(self.kind == "predict"))
+        stn = sfh_b200.STNWarpStage(tmpl.to(dev), poi.to(dev), (W, H), 4, warp_with_nearest=True)
+        stb = sfh_b200.STNWarpStage(tmpl.to(dev), poi.to(dev), (W, H), 4)
+        step_bytes = B * self.bytes_per_frame
+        self.nsets = max(2, -(-4 * L2_BYTES // step_bytes))
+        self.sets = []
+        for i in range(self.nsets):
+            th = synth.theta_family_a(B, 1234 + 17 * seed + i).to(dev)
+            s = {"theta": th, "out": {}}
+            if self.kind == "train":
+                s["gt"] = stn.predict_tail(synth.perturb(th.cpu(), seed=i).to(dev), None, False, False)["warp_mask"].to(torch.int64)
+                s["gt_poi"] = stb.transform_poi(synth.perturb(th.cpu(), seed=100 + i).to(dev)).detach()
+                nz = (torch.rand(B, poi.shape[1], generator=torch.Generator().manual_seed(i)) < 0.8).float()
+                nz[:, 0] = 1.0
+                s["nz"], s["num"] = nz.to(dev), nz.sum(1).to(dev)
+                s["w"] = torch.ones(B, dtype=torch.float64, device=dev)      # utils/dataset.py:220
+            elif self.kind == "predict":
+                s["logits"] = torch.randn(B, 4, 360, 640, device=dev)
+            self.sets.append(s)
+        del stn, stb
+
+    def step(self, i):
+        s = self.sets[i % self.nsets]
+        if self.kind == "train":
+            return self.stage.train_step(s["theta"], s["gt"], s["w"], "MSE", s["gt_poi"], s["nz"], s["num"],
+                                         1.0, 8.0, True, s["out"])
+        if self.kind == "predict":
+            return self.stage.predict_tail(s["theta"], s["logits"], True, True, s["out"])
+        r = self.stage.warp(s["theta"])
+        if self.kind == "fwd" and self.stage.court_poi is not None and self.W == 1280:
+            self.stage.transform_poi(s["theta"])
+        return r
+
+    def launches_per_step(self):
+        return 2 if (self.kind == "fwd" and self.W == 1280) else 1
+
+
+def time_workload(wl, steps, warmup, use_graph, dist_vec=None):
+    """Returns (ms_per_step over the whole timed region, mean kernel us from per-launch events)."""
+    torch = wl.torch
+    import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def one(i):
+        r = wl.step(i)
+        if multi and isinstance(r, dict) and "loss" in r:
+            dist_vec[0].copy_(r["loss"])       # local mean loss (equal shard sizes); [1] carries the count
+            dist.all_reduce(dist_vec)          # global loss numerator + frame count
+        return r
+
+    graphs = None
+    mode = "eager"
+    with torch.no_grad():
+        for i in range(max(warmup, wl.nsets)):
+            one(i)
+        torch.cuda.synchronize()
+        if use_graph and wl.kind != "fwd":
+            try:
+                graphs = []
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for i in range(wl.nsets):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=side):
+                            one(i)
+                        graphs.append(g)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                for g in graphs:
+                    g.replay()
+                torch.cuda.synchronize()
+                mode = "cuda_graph"
+            except Exception as e:      # capture unsupported in this configuration: time eagerly
+                sys.stderr.write(f"[bench] graph capture failed ({e!r}); timing eager launches\n")
+                graphs = None
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        if graphs:
+            for i in range(steps):
+                graphs[i % wl.nsets].replay()
+        else:
+            for i in range(steps):
+                one(i)
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if multi:
+            dist.barrier()
+        ms = e0.elapsed_time(e1) / steps
+        # per-launch kernel duration: an event pair around every launch, same stream, same rotation
+        n = min(steps, 200)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for i, (a, b) in enumerate(evs):
+            a.record()
+            wl.step(i)
+            b.record()
+        torch.cuda.synchronize()
+        durs = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
+        kern_us = statistics.mean(durs[: max(1, int(0.9 * n))])     # drop the slowest 10 % (launch hiccups)
+    return ms, kern_us, mode, (t0, t1)
+
+
+def time_e2e(wl, steps, warmup):
+    """Public API with HOST inputs: per step H2D of that step's inputs (pinned) and D2H of
+    loss + dtheta (train) / score + poi (predict) / nothing but a sync (fwd)."""
+    torch = wl.torch
+    dev = wl.sets[0]["theta"].device
+    host = []
+    for s in wl.sets[:2]:
+        h = {k: v.cpu().pin_memory() for k, v in s.items() if isinstance(v, torch.Tensor)}
+        host.append(h)
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    d2h = 0
+    steps = max(1, min(steps, 50))
+    res_host = {}
+
+    def one(i):
+        nonlocal d2h
+        h = host[i % len(host)]
+        d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+        if wl.kind == "train":
+            r = wl.stage.train_step(d["theta"], d["gt"], d["w"], "MSE", d["gt_poi"], d["nz"], d["num"], 1.0, 8.0, True)
+            outs = [r["loss"], r["dtheta"]]
+        elif wl.kind == "predict":
+            r = wl.stage.predict_tail(d["theta"], d["logits"], True, True)
+            outs = [r["consist_score"], r["poi"]]
+        else:
+            r = wl.stage.warp(d["theta"])
+            outs = [r.sum()]
+        got = [o.cpu() for o in outs]           # device -> host read of the step's result (syncs)
+        d2h = sum(o.numel() * o.element_size() for o in got)
+
+    with torch.no_grad():
+        for i in range(min(warmup, 3)):
+            one(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            one(i)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+    return dt, h2d, d2h
+
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    import sfh_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — sfh_b200 has no CPU path")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:          # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist_vec = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        dist_vec = torch.zeros(2, dtype=torch.float64, device=dev)
+        dist.all_reduce(dist_vec)
+
+    sfh_b200._lib.lib()                        # fail loudly if the CUDA library is missing
+    wl = Workload(args.workload, dev, seed=rank)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, kern_us, mode, (t0, t1) = time_workload(wl, args.steps, args.warmup, not args.no_graph, dist_vec)
+    clocks = sampler.finish(t0, t1)
+    t = torch.tensor([ms, kern_us], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)       # max over ranks, device-timed
+    ms, kern_us = float(t[0]), float(t[1])
+    e2e_dt, h2d, d2h = time_e2e(wl, args.steps, args.warmup)
+    t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_dt = float(t[0])
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent on this box"
+        frames = wl.B * world
+        step_bytes = wl.B * wl.bytes_per_frame
+        achieved = step_bytes / (kern_us * 1e-6) / 1e9
+        line = {
+            "metric": "warped frames/s (fwd+bwd)", "value": frames / (ms * 1e-3), "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.desc, "frames_per_step_per_gpu": wl.B, "size": [wl.W, wl.H],
+                       "launch": mode, "l2": f"inputs/outputs rotate through {wl.nsets} buffer sets "
+                                              f"({wl.nsets * step_bytes / 2**20:.0f} MiB > 4x L2); template stays L2/L1 resident by design",
+                       "parallelism": f"batch-sharded x{world}, one all-reduce of loss numerators per step" if world > 1 else "single GPU"},
+            "clocks": clocks,
+            "e2e": {"value": frames / e2e_dt, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "public API STNWarpStage.train_step with pinned host inputs; PCIe-bound on the int64 gt masks"},
+            "gpu_launches": args.steps * wl.launches_per_step(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "sfh::k_fused",
+                         "kernel_us": kern_us, "algorithmic_bytes_per_launch": step_bytes,
+                         "bytes_per_frame": wl.bytes_per_frame},
+        }
+        if world == 1 and not args.no_extra:
+            line["cpu_baseline"] = {k: v for k, v in run_cpu(args.workload, 3, 1).items()
+                                    if k in ("value", "unit", "cores", "kind", "sample")}
+            extra = {}
+            for name in WORKLOADS:
+                if name == args.workload:
+                    continue
+                try:
+                    w2 = Workload(name, dev, seed=7)
+                    m2, k2, md2, _ = time_workload(w2, 200, 10, not args.no_graph)
+                    sb = w2.B * w2.bytes_per_frame
+                    extra[name] = {"frames_per_s": w2.B / (m2 * 1e-3), "ms_per_step": m2, "kernel_us": k2,
+                                   "achieved_GBps": sb / (k2 * 1e-6) / 1e9, "frac_of_hbm_peak": sb / (k2 * 1e-6) / 1e9 / peak,
+                                   "launch": md2, "workload": w2.desc}
+                    del w2
+                    torch.cuda.empty_cache()
+                except Exception as e:
+                    extra[name] = {"error": repr(e)}
+            line["other_workloads"] = extra
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

@@ -64,6 +64,59 @@ class _PoiFn(torch.autograd.Function):
         return dth, None, None, None
 
 
+def _launch_train_tail(stage, theta9, gt_masks, kind, want_mask, gt_poi, nonzeros, num_nonzero,
+                       weights, rec_lambda, reproj_lambda, out=None):
+    """Allocate outputs (or reuse ``out``) and issue the single fused launch.  Returns a dict of
+    tensors: warp_mask, Lb, J, poi, Rb, K, loss, dtheta (absent entries are None)."""
+    B = theta9.shape[0]
+    H, W = stage.height, stage.width
+    dev = theta9.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    with_poi = stage.court_poi is not None
+    with_rep = with_poi and gt_poi is not None
+    with_loss = weights is not None
+    N = stage.court_poi.shape[1] if with_poi else 0
+    o = {} if out is None else out
+
+    def buf(name, shape, cond=True):
+        if not cond:
+            return None
+        t = o.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, **f32)
+            o[name] = t
+        return t
+
+    warp_out = buf("warp_mask", (B, H, W), want_mask)
+    Lb, J = buf("Lb", (B,)), buf("J", (B, 9))
+    poi = buf("poi", (B, N, 2), with_poi)
+    Rb, K = buf("Rb", (B,), with_rep), buf("K", (B, 9), with_rep)
+    loss, dtot = buf("loss", (), with_loss), buf("dtheta", (B, 9), with_loss)
+    xs, ys = stage.warper.grid_factors(dev)
+    ws = _WS.get(dev, B, H, W)
+    a = _lib.SfhTrainTailArgs()
+    a.theta, a.xs, a.ys, a.gt = theta9.data_ptr(), xs.data_ptr(), ys.data_ptr(), gt_masks.data_ptr()
+    a.B, a.H, a.W, a.nc, a.kind, a.N = B, H, W, stage.mask_classes, _lib.LOSS[kind], N
+    a.warp_out, a.L_b, a.dLb_dtheta = _ptr(warp_out), Lb.data_ptr(), J.data_ptr()
+    if with_poi:
+        a.court_poi, a.court_poi_bstride, a.poi_out = stage.court_poi.data_ptr(), stage.poi_bstride, poi.data_ptr()
+    if with_rep:
+        a.gt_poi, a.nonzeros, a.num_nonzero = gt_poi.data_ptr(), nonzeros.data_ptr(), num_nonzero.data_ptr()
+        a.R_b, a.dRb_dtheta = Rb.data_ptr(), K.data_ptr()
+    if with_loss:
+        a.weights = weights.data_ptr()
+        a.weights_f64 = int(weights.dtype == torch.float64)
+        a.weights_outer = int(weights.ndim == 2)
+        a.rec_lambda, a.reproj_lambda = float(rec_lambda), float(reproj_lambda)
+        a.loss_out, a.dtheta_total = loss.data_ptr(), dtot.data_ptr()
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    d = stage.template.desc()
+    with torch.cuda.device(dev):
+        rc = _lib.lib().sfh_warp_loss_fwd_bwd(d, a, _stream())
+    _lib.check(rc, "sfh_warp_loss_fwd_bwd")
+    return dict(warp_mask=warp_out, Lb=Lb, J=J, poi=poi, Rb=Rb, K=K, loss=loss, dtheta=dtot)
+
+
 class _TrainTailFn(torch.autograd.Function):
     """One launch: warp_mask, L_b (rec loss per sample), poi, R_b (reprojection per sample), the
     Jacobians J_b = dL_b/dtheta_b, K_b = dR_b/dtheta_b and — when weights are given — the
@@ -72,49 +125,16 @@ class _TrainTailFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, theta9, stage, gt_masks, kind, want_mask, gt_poi, nonzeros, num_nonzero,
                 weights, rec_lambda, reproj_lambda):
-        B = theta9.shape[0]
-        H, W = stage.height, stage.width
-        dev = theta9.device
-        f32 = dict(dtype=torch.float32, device=dev)
-        with_poi = stage.court_poi is not None
-        with_rep = with_poi and gt_poi is not None
-        with_loss = weights is not None
-        N = stage.court_poi.shape[1] if with_poi else 0
-        warp_out = torch.empty((B, H, W), **f32) if want_mask else None
-        Lb, J = torch.empty(B, **f32), torch.empty((B, 9), **f32)
-        poi = torch.empty((B, N, 2), **f32) if with_poi else None
-        Rb = torch.empty(B, **f32) if with_rep else None
-        K = torch.empty((B, 9), **f32) if with_rep else None
-        loss = torch.empty((), **f32) if with_loss else None
-        dtot = torch.empty((B, 9), **f32) if with_loss else None
-        xs, ys = stage.warper.grid_factors(dev)
-        ws = _WS.get(dev, B, H, W)
-        a = _lib.SfhTrainTailArgs()
-        a.theta, a.xs, a.ys, a.gt = theta9.data_ptr(), xs.data_ptr(), ys.data_ptr(), gt_masks.data_ptr()
-        a.B, a.H, a.W, a.nc, a.kind, a.N = B, H, W, stage.mask_classes, _lib.LOSS[kind], N
-        a.warp_out, a.L_b, a.dLb_dtheta = _ptr(warp_out), Lb.data_ptr(), J.data_ptr()
-        if with_poi:
-            a.court_poi, a.court_poi_bstride, a.poi_out = stage.court_poi.data_ptr(), stage.poi_bstride, poi.data_ptr()
-        if with_rep:
-            a.gt_poi, a.nonzeros, a.num_nonzero = gt_poi.data_ptr(), nonzeros.data_ptr(), num_nonzero.data_ptr()
-            a.R_b, a.dRb_dtheta = Rb.data_ptr(), K.data_ptr()
-        if with_loss:
-            a.weights = weights.data_ptr()
-            a.weights_f64 = int(weights.dtype == torch.float64)
-            a.weights_outer = int(weights.ndim == 2)
-            a.rec_lambda, a.reproj_lambda = float(rec_lambda), float(reproj_lambda)
-            a.loss_out, a.dtheta_total = loss.data_ptr(), dtot.data_ptr()
-        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-        d = stage.template.desc()
-        with torch.cuda.device(dev):
-            rc = _lib.lib().sfh_warp_loss_fwd_bwd(d, a, _stream())
-        _lib.check(rc, "sfh_warp_loss_fwd_bwd")
-        ctx.save_for_backward(theta9, J, K if with_rep else J, dtot if with_loss else J)
+        r = _launch_train_tail(stage, theta9, gt_masks, kind, want_mask, gt_poi, nonzeros, num_nonzero,
+                               weights, rec_lambda, reproj_lambda)
+        with_poi, with_rep, with_loss = r["poi"] is not None, r["Rb"] is not None, r["loss"] is not None
+        J = r["J"]
+        ctx.save_for_backward(theta9, J, r["K"] if with_rep else J, r["dtheta"] if with_loss else J)
         ctx.with_rep, ctx.with_poi, ctx.with_loss, ctx.stage = with_rep, with_poi, with_loss, stage
         ctx.set_materialize_grads(False)       # unused outputs arrive as None: no zero-fill, no sync
-        e = Lb.new_empty(0)
-        outs = (warp_out if want_mask else e, Lb, poi if with_poi else e, Rb if with_rep else e,
-                loss if with_loss else e)
+        e = J.new_empty(0)
+        outs = (r["warp_mask"] if want_mask else e, r["Lb"], r["poi"] if with_poi else e,
+                r["Rb"] if with_rep else e, r["loss"] if with_loss else e)
         ctx.mark_non_differentiable(outs[0])
         return outs
 
@@ -203,9 +223,17 @@ class STNWarpStage(torch.nn.Module):
 
     forward = forward_tail
 
+    def _buf(self, out, name, shape, dtype):
+        t = None if out is None else out.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            if out is not None:
+                out[name] = t
+        return t
+
     @torch.no_grad()
     def predict_tail(self, theta: torch.Tensor, logits: Optional[torch.Tensor] = None,
-                     consistency: bool = True, project_poi: bool = False) -> dict:
+                     consistency: bool = True, project_poi: bool = False, out: Optional[dict] = None) -> dict:
         """Warp-stage part of Reconstructor.predict (models/reconstructor.py:221-245):
         int32 warp_mask (= warp*mask_classes), consist_score [B], optional poi — one launch."""
         theta9 = check_theta(theta, self.device)
@@ -218,11 +246,11 @@ class STNWarpStage(torch.nn.Module):
             if logits.ndim != 4 or logits.shape[0] != B or logits.shape[1] != self.mask_classes:
                 raise ValueError(f"logits must be [B,{self.mask_classes},h,w], got {tuple(logits.shape)}")
             h, w = logits.shape[2:]
-            score = torch.empty(B, dtype=torch.float32, device=self.device)
+            score = self._buf(out, "consist_score", (B,), torch.float32)
         want_poi = project_poi and self.court_poi is not None
         N = self.court_poi.shape[1] if want_poi else 0
-        poi = torch.empty((B, N, 2), dtype=torch.float32, device=self.device) if want_poi else None
-        mask = torch.empty((B, H, W), dtype=torch.int32, device=self.device)
+        poi = self._buf(out, "poi", (B, N, 2), torch.float32) if want_poi else None
+        mask = self._buf(out, "warp_mask", (B, H, W), torch.int32)
         xs, ys = self.warper.grid_factors(self.device)
         ws = _WS.get(self.device, B, H, W)
         a = _lib.SfhPredictTailArgs()
@@ -245,23 +273,7 @@ class STNWarpStage(torch.nn.Module):
             ret["poi"] = poi
         return ret
 
-    def train_tail(self, theta: torch.Tensor, gt_masks: torch.Tensor, rec_loss: str = "MSE",
-                   gt_poi: Optional[torch.Tensor] = None, nonzeros: Optional[torch.Tensor] = None,
-                   num_nonzero: Optional[torch.Tensor] = None, want_mask: bool = True,
-                   weights: Optional[torch.Tensor] = None, rec_lambda: float = 1.0,
-                   reproj_lambda: float = 1.0) -> dict:
-        """Fused training tail.  Returns per-sample terms so the caller applies the reference's own
-        weighting / reduction (models/losses.py:38-39 broadcasting quirk included):
-
-            rec_per_sample    [B]  = mean_{h,w} crit(warp_mask, gt_masks/nc)     (train.py:195-196)
-            reproj_per_sample [B]  = sum_n ||gt_poi-poi|| nonzeros / num_nonzero (models/losses.py:10-11)
-            warp_mask [B,H,W] fp32 (no gradient flows through it on this path), poi [B,N,2]
-
-        With ``weights`` (the batch's ``gt_weights``: fp64 [B] or fp32 [B,1], train.py:159) the same
-        launch also returns the reference's scalar
-            loss = rec_lambda * mean(rec_per_sample * weights) + reproj_lambda * mean(reproj_per_sample)
-        (plain broadcasting, so [B,1] weights reproduce the [B,B] quirk) with d loss / d theta.
-        """
+    def _check_train_args(self, theta, gt_masks, rec_loss, gt_poi, nonzeros, num_nonzero, weights):
         if self.mode != "bilinear":
             raise ValueError("train_tail needs a bilinear warper (nearest has no gradient)")
         if rec_loss not in _lib.LOSS:
@@ -290,6 +302,50 @@ class STNWarpStage(torch.nn.Module):
             if not (tuple(weights.shape) == (B,) or tuple(weights.shape) == (B, 1)):
                 raise ValueError(f"weights must be [B] or [B,1], got {tuple(weights.shape)}")
             weights = weights.contiguous()
+        return theta9, gt_masks, gt_poi, nonzeros, num_nonzero, weights
+
+    @torch.no_grad()
+    def train_step(self, theta: torch.Tensor, gt_masks: torch.Tensor, weights: torch.Tensor,
+                   rec_loss: str = "MSE", gt_poi: Optional[torch.Tensor] = None,
+                   nonzeros: Optional[torch.Tensor] = None, num_nonzero: Optional[torch.Tensor] = None,
+                   rec_lambda: float = 1.0, reproj_lambda: float = 1.0, want_mask: bool = True,
+                   out: Optional[dict] = None) -> dict:
+        """Forward AND backward of the warp stage in one launch, without autograd bookkeeping:
+        returns {'loss' (scalar), 'dtheta' [B,3,3] = d loss / d theta, 'warp_mask', 'poi',
+        'rec_per_sample', 'reproj_per_sample'} for
+            loss = rec_lambda * mean(L_b * weights) + reproj_lambda * mean(R_b)
+        (train.py:194-197,209-214).  ``out`` may carry buffers from a previous call for reuse."""
+        theta9, gt_masks, gt_poi, nonzeros, num_nonzero, weights = self._check_train_args(
+            theta, gt_masks, rec_loss, gt_poi, nonzeros, num_nonzero, weights)
+        if weights is None:
+            raise ValueError("train_step needs the per-sample weights (use ones for an unweighted mean)")
+        r = _launch_train_tail(self, theta9, gt_masks, rec_loss, want_mask, gt_poi, nonzeros, num_nonzero,
+                               weights, rec_lambda, reproj_lambda, out)
+        ret = {"loss": r["loss"], "dtheta": r["dtheta"].view(-1, 3, 3), "rec_per_sample": r["Lb"]}
+        for k_out, k_in in (("warp_mask", "warp_mask"), ("poi", "poi"), ("reproj_per_sample", "Rb")):
+            if r[k_in] is not None:
+                ret[k_out] = r[k_in]
+        return ret
+
+    def train_tail(self, theta: torch.Tensor, gt_masks: torch.Tensor, rec_loss: str = "MSE",
+                   gt_poi: Optional[torch.Tensor] = None, nonzeros: Optional[torch.Tensor] = None,
+                   num_nonzero: Optional[torch.Tensor] = None, want_mask: bool = True,
+                   weights: Optional[torch.Tensor] = None, rec_lambda: float = 1.0,
+                   reproj_lambda: float = 1.0) -> dict:
+        """Fused training tail.  Returns per-sample terms so the caller applies the reference's own
+        weighting / reduction (models/losses.py:38-39 broadcasting quirk included):
+
+            rec_per_sample    [B]  = mean_{h,w} crit(warp_mask, gt_masks/nc)     (train.py:195-196)
+            reproj_per_sample [B]  = sum_n ||gt_poi-poi|| nonzeros / num_nonzero (models/losses.py:10-11)
+            warp_mask [B,H,W] fp32 (no gradient flows through it on this path), poi [B,N,2]
+
+        With ``weights`` (the batch's ``gt_weights``: fp64 [B] or fp32 [B,1], train.py:159) the same
+        launch also returns the reference's scalar
+            loss = rec_lambda * mean(rec_per_sample * weights) + reproj_lambda * mean(reproj_per_sample)
+        (plain broadcasting, so [B,1] weights reproduce the [B,B] quirk) with d loss / d theta.
+        """
+        theta9, gt_masks, gt_poi, nonzeros, num_nonzero, weights = self._check_train_args(
+            theta, gt_masks, rec_loss, gt_poi, nonzeros, num_nonzero, weights)
         mask, Lb, poi, Rb, loss = _TrainTailFn.apply(theta9, self, gt_masks, rec_loss, want_mask,
                                                      gt_poi, nonzeros, num_nonzero, weights,
                                                      rec_lambda, reproj_lambda)
