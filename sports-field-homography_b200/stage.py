@@ -171,17 +171,19 @@ class STNWarpStage(torch.nn.Module):
     Arguments mirror the corresponding ``Reconstructor.__init__`` ones
     (models/reconstructor.py:36-49): ``court_img`` [B,1,Hc,Wc] fp32 CUDA, ``court_poi`` [B,N,2]
     fp32 CUDA in [-1,1] (or None), ``warp_size`` (W,H), ``mask_classes``, ``warp_with_nearest``.
+    ``grid_source`` selects whose meshgrid rounding is replayed (see ``meshgrid_factors``).
     """
 
     def __init__(self, court_img: torch.Tensor, court_poi: Optional[torch.Tensor] = None,
-                 warp_size=(640, 360), mask_classes: int = 4, warp_with_nearest: bool = False):
+                 warp_size=(640, 360), mask_classes: int = 4, warp_with_nearest: bool = False,
+                 grid_source: str = "device"):
         super().__init__()
         self.width, self.height = int(warp_size[0]), int(warp_size[1])
         self.mask_classes = int(mask_classes)
         self.mode = "nearest" if warp_with_nearest else "bilinear"
         # plain attributes, like the reference: nothing enters state_dict()
         self.court_img = court_img
-        self.warper = HomographyWarper(self.height, self.width, mode=self.mode)
+        self.warper = HomographyWarper(self.height, self.width, mode=self.mode, grid_source=grid_source)
         self.template: CourtTemplate = self.warper.set_template(court_img)
         self.device = court_img.device
         if court_poi is not None:

@@ -58,15 +58,21 @@ class _Workspace:
 _WS = _Workspace()
 
 
-def meshgrid_factors(height: int, width: int, device, dtype=torch.float32):
+def meshgrid_factors(height: int, width: int, device, dtype=torch.float32, grid_source: str = "device"):
     """1-D factors of kornia's create_meshgrid(normalized_coordinates=True), built with the same
-    torch ops on the same device as kornia does, so the bits equal the reference's on that device
-    (ATen's CUDA division-by-scalar multiplies by the reciprocal; its CPU one divides)."""
-    xs = torch.linspace(0, width - 1, width, device=device, dtype=dtype)
-    ys = torch.linspace(0, height - 1, height, device=device, dtype=dtype)
+    torch ops kornia uses.  ATen's CUDA ``tensor / python_scalar`` multiplies by the reciprocal
+    while its CPU one divides, so the two devices disagree by an ulp on some columns (measured on
+    B200: that is the ONLY difference between the reference run on GPU and on CPU; everything
+    downstream is replayed bit for bit by the kernels).  ``grid_source='device'`` (default)
+    reproduces the reference executed on this GPU, ``'cpu'`` the reference executed on the host."""
+    if grid_source not in ("device", "cpu"):
+        raise ValueError("grid_source must be 'device' or 'cpu'")
+    build_on = device if grid_source == "device" else torch.device("cpu")
+    xs = torch.linspace(0, width - 1, width, device=build_on, dtype=dtype)
+    ys = torch.linspace(0, height - 1, height, device=build_on, dtype=dtype)
     xs = (xs / (width - 1) - 0.5) * 2
     ys = (ys / (height - 1) - 0.5) * 2
-    return xs.contiguous(), ys.contiguous()
+    return xs.to(device).contiguous(), ys.to(device).contiguous()
 
 
 class _WarpFn(torch.autograd.Function):
@@ -116,8 +122,12 @@ class HomographyWarper(torch.nn.Module):
     """
 
     def __init__(self, height: int, width: int, mode: str = "bilinear", padding_mode: str = "zeros",
-                 normalized_coordinates: bool = True, align_corners: bool = False) -> None:
+                 normalized_coordinates: bool = True, align_corners: bool = False,
+                 grid_source: str = "device") -> None:
         super().__init__()
+        if grid_source not in ("device", "cpu"):
+            raise ValueError("grid_source must be 'device' or 'cpu'")
+        self.grid_source = grid_source
         if mode not in ("bilinear", "nearest"):
             raise NotImplementedError(f"mode={mode!r}: only 'bilinear' and 'nearest' are implemented")
         if padding_mode != "zeros" or not normalized_coordinates or align_corners:
@@ -132,7 +142,7 @@ class HomographyWarper(torch.nn.Module):
     def grid_factors(self, device):
         g = self._grid.get(device)
         if g is None:
-            g = meshgrid_factors(self.height, self.width, device)
+            g = meshgrid_factors(self.height, self.width, device, grid_source=self.grid_source)
             self._grid[device] = g
         return g
 

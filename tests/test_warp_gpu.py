@@ -36,6 +36,13 @@ def cu(a, dtype=None):
     return t.to(DEV)
 
 
+def mk_stage(*a, grid_source="cpu", **k):
+    """Tests compare against CPU-built oracles / golden vectors, so by default the stage replays
+    the CPU meshgrid rounding; `grid_source="device"` is checked against ATen run on the GPU
+    (see sfh_b200.meshgrid_factors: this is the only fp32 difference between the two)."""
+    return sfh_b200.STNWarpStage(*a, grid_source=grid_source, **k)
+
+
 def relnorm(a, b):
     a = np.asarray(a, np.float64).reshape(a.shape[0], -1)
     b = np.asarray(b, np.float64).reshape(b.shape[0], -1)
@@ -58,30 +65,26 @@ def test_golden_small_all_outputs(golden_small):
     poi = cu(g["court_poi"])[None].repeat(B, 1, 1)
     th = cu(g["theta"])
     for nearest, key in ((False, "warp_bilinear"), (True, "warp_nearest")):
-        st = sfh_b200.STNWarpStage(tmpl, poi, (W, H), 4, warp_with_nearest=nearest)
+        st = mk_stage(tmpl, poi, (W, H), 4, warp_with_nearest=nearest)
         out = st.warp(th).cpu().numpy()
         assert out.shape == (B, H, W)
         if nearest:
             assert np.array_equal(out, g[key])
         else:
             assert np.abs(out - g[key]).max() <= TOL_MASK
-    st = sfh_b200.STNWarpStage(tmpl, poi, (W, H), 4)
+    st = mk_stage(tmpl, poi, (W, H), 4)
     p = st.transform_poi(th).cpu().numpy()
     assert np.abs(p - g["poi"]).max() * W <= 2e-3 * 1   # vs reference fp32 LU (its own noise); see fp64 test
     # predict tail through the fused launch
     for tag in ("half", "full", "odd"):
         for mode in ("nearest", "bilinear"):
-            stp = sfh_b200.STNWarpStage(tmpl, poi, (W, H), 4, warp_with_nearest=(mode == "nearest"))
+            stp = mk_stage(tmpl, poi, (W, H), 4, warp_with_nearest=(mode == "nearest"))
             r = stp.predict_tail(th, cu(g[f"pred_{tag}_logits"]), consistency=True, project_poi=True)
             assert r["warp_mask"].dtype == torch.int32 and r["consist_score"].dtype == torch.float32
             m = r["warp_mask"].cpu().numpy()
             ref = g[f"pred_{tag}_{mode}_mask"]
-            if mode == "nearest":
-                assert np.array_equal(m, ref), (tag, mode)
-            else:
-                assert (m != ref).mean() < 1e-3
-            np.testing.assert_allclose(r["consist_score"].cpu().numpy(), g[f"pred_{tag}_{mode}_score"],
-                                       rtol=1e-5 if mode == "nearest" else 2e-3)
+            assert np.array_equal(m, ref), (tag, mode, (m != ref).mean())
+            np.testing.assert_allclose(r["consist_score"].cpu().numpy(), g[f"pred_{tag}_{mode}_score"], rtol=1e-5)
             assert np.abs(r["poi"].cpu().numpy() - g[f"pred_{tag}_{mode}_poi"]).max() * W <= 2e-3
 
 
@@ -91,7 +94,7 @@ def test_golden_small_losses_and_gradients(golden_small):
     H, W = g["template"].shape
     tmpl = cu(g["template"])[None, None].repeat(B, 1, 1, 1)
     poi = cu(g["court_poi"])[None].repeat(B, 1, 1)
-    st = sfh_b200.STNWarpStage(tmpl, poi, (W, H), 4)
+    st = mk_stage(tmpl, poi, (W, H), 4)
     gt = cu(g["gt"])
     for kind, name in (("MSE", "mse"), ("SmoothL1", "sl1")):
         for wn in ("w1", "w2"):
@@ -152,9 +155,9 @@ def test_golden_real_thetas(golden_real):
     for (W, H) in [(640, 360), (1280, 720)]:
         tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (W, H), 4, 2)
         tmpl, poi = tmpl.to(DEV), poi.to(DEV)
-        r = sfh_b200.STNWarpStage(tmpl, poi, (W, H), 4, warp_with_nearest=True).predict_tail(th, None, False, True)
+        r = mk_stage(tmpl, poi, (W, H), 4, warp_with_nearest=True).predict_tail(th, None, False, True)
         assert np.array_equal(r["warp_mask"].cpu().numpy(), unpack2(g[f"nearest_{W}x{H}_bits"], (2, H, W)))
-        wb = sfh_b200.STNWarpStage(tmpl, poi, (W, H), 4).warp(th).cpu().numpy()
+        wb = mk_stage(tmpl, poi, (W, H), 4).warp(th).cpu().numpy()
         assert np.abs(wb[:, ::7, ::5] - g[f"bilinear_{W}x{H}_sample"]).max() <= TOL_MASK
         np.testing.assert_allclose(wb.astype(np.float64).sum((1, 2)), g[f"bilinear_{W}x{H}_sum"], rtol=1e-6)
         p64 = co.poi_fwd(g["theta"], poi.cpu().numpy())
@@ -186,25 +189,28 @@ def test_warp_forward_matches_oracles(W, H, B, fam, scale, mode):
     th = _thetas(fam, B, 100 + W) * scale
     ref_c = co.warp_fwd(th.numpy(), tmpl.numpy(), H, W, mode)[:, 0]
     d_t = tmpl.to(DEV)
-    packed = sfh_b200.STNWarpStage(d_t, None, (W, H), 4, warp_with_nearest=(mode == "nearest"))
+    th_d = th.to(DEV)
+    # (1) grid_source='cpu': must reproduce the reference executed on the host (C oracle == ATen CPU)
+    packed = mk_stage(d_t, None, (W, H), 4, warp_with_nearest=(mode == "nearest"))
     assert packed.template.fmt == sfh_b200._lib.TMPL_Q2
-    out_q = packed.warp(th.to(DEV)).cpu().numpy()
-    wf = sfh_b200.HomographyWarper(H, W, mode=mode)
-    out_f = wf(d_t.expand(B, -1, -1, -1), th.to(DEV))[:, 0].cpu().numpy()      # plain fp32 template path
-    # reference executed on this GPU by stock ATen (what the reference really runs)
-    ref_g = kr.HomographyWarper(H, W, mode=mode)(d_t.expand(B, -1, -1, -1), th.to(DEV))[:, 0].cpu().numpy()
+    out_q = packed.warp(th_d).cpu().numpy()
+    wf = sfh_b200.HomographyWarper(H, W, mode=mode, grid_source="cpu")
+    out_f = wf(d_t.expand(B, -1, -1, -1), th_d)[:, 0].cpu().numpy()      # plain fp32 template path
     assert np.array_equal(out_q, out_f)            # template format must not change a single bit
+    # (2) grid_source='device' (default): must reproduce the reference executed on this GPU
+    dev_stage = mk_stage(d_t, None, (W, H), 4, warp_with_nearest=(mode == "nearest"), grid_source="device")
+    out_d = dev_stage.warp(th_d).cpu().numpy()
+    ref_g = kr.HomographyWarper(H, W, mode=mode)(d_t.expand(B, -1, -1, -1), th_d)[:, 0].cpu().numpy()
     if mode == "nearest":
-        # bit-exact vs the oracle except flips on exact rounding ties of the sampling coordinate
-        for ref in (ref_c, ref_g):
-            assert (out_q != ref).mean() <= 2e-6, (out_q != ref).mean()
+        assert np.array_equal(out_q, ref_c), (out_q != ref_c).mean()     # bit-exact
+        assert np.array_equal(out_d, ref_g), (out_d != ref_g).mean()
     else:
-        bad_c = np.abs(out_q - ref_c) > TOL_MASK
-        bad_g = np.abs(out_q - ref_g) > TOL_MASK
-        # the kernel replays ATen's op order: it must agree with ATen-on-GPU within tolerance
-        # everywhere; vs the CPU oracle only meshgrid-division rounding may differ (edge pixels)
-        assert bad_g.mean() == 0.0, (bad_g.mean(), np.abs(out_q - ref_g).max())
-        assert bad_c.mean() <= 5e-3, bad_c.mean()
+        assert np.abs(out_q - ref_c).max() <= TOL_MASK, np.abs(out_q - ref_c).max()
+        assert np.abs(out_d - ref_g).max() <= TOL_MASK, np.abs(out_d - ref_g).max()
+    # the two references differ from each other (ATen CUDA meshgrid multiplies by 1/(W-1)):
+    # report, don't assert a direction
+    print(f"[info] {W}x{H} {mode}: ATen-GPU vs ATen-CPU reference differ on "
+          f"{(np.abs(ref_g - ref_c) > TOL_MASK).mean():.2e} of pixels (max {np.abs(ref_g - ref_c).max():.1e})")
 
 
 def test_q4_palette_and_float_templates():
@@ -214,22 +220,22 @@ def test_q4_palette_and_float_templates():
     cls = rng.integers(0, 8, size=(36, 64)).repeat(4, 0).repeat(4, 1)
     tmpl = torch.from_numpy((cls / 8.0).astype(np.float32))[None, None]
     th = synth.theta_family_a(B, 3)
-    st = sfh_b200.STNWarpStage(tmpl.to(DEV), None, (W, H), 8)
+    st = mk_stage(tmpl.to(DEV), None, (W, H), 8)
     assert st.template.fmt == sfh_b200._lib.TMPL_Q4
     ref = co.warp_fwd(th.numpy(), tmpl.numpy(), H, W)[:, 0]
     assert np.abs(st.warp(th.to(DEV)).cpu().numpy() - ref).max() <= TOL_MASK
     t7 = torch.from_numpy((rng.integers(0, 7, size=(40, 60)) / 7.0).astype(np.float32))[None, None]
-    st7 = sfh_b200.STNWarpStage(t7.to(DEV), None, (W, H), 7)
+    st7 = mk_stage(t7.to(DEV), None, (W, H), 7)
     ref7 = co.warp_fwd(th.numpy(), t7.numpy(), H, W)[:, 0]
     assert np.abs(st7.warp(th.to(DEV)).cpu().numpy() - ref7).max() <= TOL_MASK
     ft = torch.from_numpy(rng.random((B, 3, 45, 80), dtype=np.float32))
-    out = sfh_b200.HomographyWarper(H, W)(ft.to(DEV), th.to(DEV)).cpu().numpy()
+    out = sfh_b200.HomographyWarper(H, W, grid_source="cpu")(ft.to(DEV), th.to(DEV)).cpu().numpy()
     assert np.abs(out - co.warp_fwd(th.numpy(), ft.numpy(), H, W)).max() <= TOL_MASK
-    outn = sfh_b200.HomographyWarper(H, W, mode="nearest")(ft.to(DEV), th.to(DEV)).cpu().numpy()
-    assert (outn != co.warp_fwd(th.numpy(), ft.numpy(), H, W, "nearest")).mean() < 1e-5
+    outn = sfh_b200.HomographyWarper(H, W, mode="nearest", grid_source="cpu")(ft.to(DEV), th.to(DEV)).cpu().numpy()
+    assert np.array_equal(outn, co.warp_fwd(th.numpy(), ft.numpy(), H, W, "nearest"))
     # backward through a multi-channel float template
     thg = th.to(DEV).requires_grad_(True)
-    o = sfh_b200.HomographyWarper(H, W)(ft.to(DEV), thg)
+    o = sfh_b200.HomographyWarper(H, W, grid_source="cpu")(ft.to(DEV), thg)
     go = torch.randn(o.shape, generator=torch.Generator().manual_seed(1))
     o.backward(go.to(DEV))
     ref = co.warp_bwd(th.numpy(), ft.numpy(), go.numpy())
@@ -250,7 +256,7 @@ def test_fused_train_tail_matches_oracle(W, H, B, fam, kind):
     nz = (rng.random((B, poi.shape[1])) < 0.8).astype(np.float32)
     nz[:, 0] = 1
     num = nz.sum(1)
-    st = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (W, H), 4)
+    st = mk_stage(tmpl.to(DEV), poi.to(DEV), (W, H), 4)
     thg = th.to(DEV).requires_grad_(True)
     r = st.train_tail(thg, cu(gt), kind, cu(gt_poi), cu(nz), cu(num))
     assert np.abs(r["warp_mask"].cpu().numpy() - warp_ref).max() <= TOL_MASK
@@ -287,7 +293,7 @@ def test_reprojection_gradient_matches_fp64_autograd():
     l64 = kr.reprojection_loss(kr.transform_poi(t64, poi.double()), gt_poi, nz, num, "sum")
     l64.backward()
     tmpl, _ = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 1)
-    st = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (640, 360), 4)
+    st = mk_stage(tmpl.to(DEV), poi.to(DEV), (640, 360), 4)
     tg = th.to(DEV).requires_grad_(True)
     p = st.transform_poi(tg)
     l = sfh_b200.reprojection_loss(p, gt_poi.float().to(DEV), nz.float().to(DEV), num.float().to(DEV), "sum")
@@ -305,11 +311,10 @@ def test_predict_tail_matches_oracle(W, H, B, name):
     lh, lw = 360, 640
     logits = torch.randn(B, 4, lh, lw, generator=torch.Generator().manual_seed(8))
     m_ref, s_ref = co.predict_tail(th.numpy(), tmpl.numpy(), logits.numpy(), 4, H, W, "nearest")
-    st = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, warp_with_nearest=True)
+    st = mk_stage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, warp_with_nearest=True)
     r = st.predict_tail(th.to(DEV), logits.to(DEV), consistency=True, project_poi=True)
     m = r["warp_mask"].cpu().numpy()
-    flips = (m != m_ref).mean()
-    assert flips <= 2e-6, flips
+    assert np.array_equal(m, m_ref), (m != m_ref).mean()
     np.testing.assert_allclose(r["consist_score"].cpu().numpy(), s_ref, rtol=1e-5)
     p64 = co.poi_fwd(th.numpy(), poi.expand(B, -1, -1).numpy())
     assert np.abs(r["poi"].cpu().numpy() - p64).max() * W <= TOL_POI_PX
@@ -344,8 +349,8 @@ def test_properties_at_full_size():
     W, H, B = 1280, 720, 32
     tmpl, poi = sfh_b200.load_bundled("pitch_v3_nc4", (W, H), 4, 1)      # C4
     th = synth.theta_family_b(B, 77).to(DEV)
-    stn = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, warp_with_nearest=True)
-    stb = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (W, H), 4)
+    stn = mk_stage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, warp_with_nearest=True)
+    stb = mk_stage(tmpl.to(DEV), poi.to(DEV), (W, H), 4)
     a = stn.predict_tail(th, None, False, True)
     b = stn.predict_tail(th, None, False, True)
     assert torch.equal(a["warp_mask"], b["warp_mask"]) and torch.equal(a["poi"], b["poi"])   # deterministic
@@ -380,7 +385,7 @@ def test_nonfinite_and_degenerate_theta():
     th[2, 0, 2, 2] = 1e-9                   # |z| <= eps -> scale = 1
     th[2, 0, 2, 0] = 0.0
     th[3, 0] *= 1e30                        # huge but finite
-    st = sfh_b200.STNWarpStage(tmpl.to(DEV), None, (W, H), 4)
+    st = mk_stage(tmpl.to(DEV), None, (W, H), 4)
     out = st.warp(th.to(DEV)).cpu().numpy()
     ref = co.warp_fwd(th.numpy(), tmpl.numpy(), H, W)[:, 0]
     assert float(np.abs(out[0]).max()) == 0.0 and float(np.abs(out[1]).max()) == 0.0
@@ -390,7 +395,7 @@ def test_nonfinite_and_degenerate_theta():
 # ---------------------------------------------------------------------- API / error conventions
 def test_error_conventions_and_state_dict():
     tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 2)
-    st = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (640, 360), 4)
+    st = mk_stage(tmpl.to(DEV), poi.to(DEV), (640, 360), 4)
     assert len(st.state_dict()) == 0                       # court_img / court_poi are plain attributes
     with pytest.raises(TypeError):
         st.warp(torch.eye(3)[None])                        # CPU theta: no CPU path

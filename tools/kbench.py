@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Development micro-benchmark: per-launch CUDA-event time of each fused launch at the BASELINE
+sizes (not the bench contract; bench.py is).  Usage: python tools/kbench.py [--only train] [--n 30]"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import sfh_b200  # noqa: E402
+from sfh_b200 import synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--only", default="")
+ap.add_argument("--n", type=int, default=30)
+ap.add_argument("--sets", type=int, default=4)
+ap.add_argument("--hd", action="store_true")
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+PEAK = 6545.3
+
+
+def run(tag, fn, nbytes):
+    if a.only and a.only not in tag:
+        return
+    for i in range(3):
+        fn(i)
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.n)]
+    for i, (e0, e1) in enumerate(evs):
+        e0.record()
+        fn(i)
+        e1.record()
+    torch.cuda.synchronize()
+    us = sorted(e0.elapsed_time(e1) * 1e3 for e0, e1 in evs)
+    med = statistics.median(us)
+    print(f"{tag:34s} med {med:8.1f} us  min {us[0]:8.1f} us  {nbytes / med / 1e3:7.0f} GB/s  {nbytes / med / 1e3 / PEAK * 100:5.1f} % of HBM peak", flush=True)
+
+
+cfgs = [(640, 360, 64)] + ([(1280, 720, 32)] if a.hd else [])
+for (W, H, B) in cfgs:
+    tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (W, H), 4, 1)
+    stb = sfh_b200.STNWarpStage(tmpl.to(dev), poi.to(dev), (W, H), 4)
+    stn = sfh_b200.STNWarpStage(tmpl.to(dev), poi.to(dev), (W, H), 4, warp_with_nearest=True)
+    sets = []
+    for i in range(a.sets):
+        th = synth.theta_family_a(B, 50 + i).to(dev)
+        gt = stn.predict_tail(synth.perturb(th.cpu(), seed=i).to(dev), None, False, False)["warp_mask"].to(torch.int64)
+        gt_poi = stb.transform_poi(synth.perturb(th.cpu(), seed=9).to(dev)).detach()
+        nz = torch.ones(B, poi.shape[1], device=dev)
+        sets.append(dict(th=th, gt=gt, gt_poi=gt_poi, nz=nz, num=nz.sum(1), w=torch.ones(B, dtype=torch.float64, device=dev),
+                         logits=torch.randn(B, 4, 360, 640, device=dev), out={}, outp={}))
+    px = B * H * W
+    S = lambda i: sets[i % len(sets)]
+    with torch.no_grad():
+        run(f"store_bilinear_{W}x{H}_B{B}", lambda i: stb.warp(S(i)["th"]), px * 4)
+        run(f"store_nearest_{W}x{H}_B{B}", lambda i: stn.warp(S(i)["th"]), px * 4)
+        run(f"train_{W}x{H}_B{B}", lambda i: stb.train_step(S(i)["th"], S(i)["gt"], S(i)["w"], "MSE", S(i)["gt_poi"], S(i)["nz"], S(i)["num"], 1.0, 8.0, True, S(i)["out"]), px * 12)
+        run(f"train_nomask_{W}x{H}_B{B}", lambda i: stb.train_step(S(i)["th"], S(i)["gt"], S(i)["w"], "MSE", S(i)["gt_poi"], S(i)["nz"], S(i)["num"], 1.0, 8.0, False, S(i)["out"]), px * 8)
+        run(f"predict_{W}x{H}_B{B}", lambda i: stn.predict_tail(S(i)["th"], S(i)["logits"], True, True, S(i)["outp"]), px * 4 + B * 4 * 360 * 640 * 4)
+        run(f"predict_noscore_{W}x{H}_B{B}", lambda i: stn.predict_tail(S(i)["th"], None, False, False, S(i)["outp"]), px * 4)
+        go = torch.randn(B, 1, H, W, device=dev)
+        thg = S(0)["th"]
+        def bwd(i):
+            t = S(i)["th"].clone().requires_grad_(True)
+            with torch.enable_grad():
+                o = stb.warper(stb.court_img, t)
+            o.backward(go)
+        run(f"fwd+generic_bwd_{W}x{H}_B{B}", bwd, px * 12)
