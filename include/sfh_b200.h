@@ -44,19 +44,20 @@ extern "C" {
 
 /* template storage formats */
 #define SFH_TMPL_F32 0  /* [Bt,C,Hc,Wc] fp32 as open_court_template returns it (utils/dataset.py:47-61) */
-#define SFH_TMPL_Q2  1  /* quad-packed palette indices, 2 bits/tap, uint8  [(Hc+1) x pitch] */
-#define SFH_TMPL_Q4  2  /* quad-packed palette indices, 4 bits/tap, uint16 [(Hc+1) x pitch] */
+#define SFH_TMPL_Q2  1  /* quad-packed palette indices, 2 bits/tap, uint8  [(Hc+2) x pitch] */
+#define SFH_TMPL_Q4  2  /* quad-packed palette indices, 4 bits/tap, uint16 [(Hc+2) x pitch] */
 
-/* Template descriptor.  For Q2/Q4, entry (j,i) holds the palette indices of the 2x2
- * neighbourhood whose top-left texel is (y=j-1, x=i-1); texels outside the image are palette
- * index 0 and palette[0] must be 0.0f (= padding_mode='zeros').  C must be 1 for Q2/Q4. */
+/* Template descriptor.  For Q2/Q4, entry (j,i), 0 <= j <= Hc+1, 0 <= i <= Wc+1, holds the palette
+ * indices of the 2x2 neighbourhood whose top-left texel is (y=j-1, x=i-1); texels outside the
+ * image are palette index 0 and palette[0] must be 0.0f (= padding_mode='zeros'), so the last
+ * row and column are all zero and serve as the clamp target.  C must be 1 for Q2/Q4. */
 typedef struct sfh_template {
     const void* data;        /* device pointer */
     int32_t     fmt;         /* SFH_TMPL_* */
     int32_t     channels;    /* C */
     int32_t     height;      /* Hc */
     int32_t     width;       /* Wc */
-    int32_t     pitch;       /* Q2/Q4: elements per packed row (>= Wc+1); F32: ignored */
+    int32_t     pitch;       /* Q2/Q4: elements per packed row (>= Wc+2); F32: ignored */
     int32_t     n_palette;   /* Q2/Q4: number of valid palette entries */
     int64_t     batch_stride;/* F32: elements between consecutive samples, 0 = one shared template */
     float       palette[16]; /* Q2/Q4: texel value of each palette index */
@@ -184,6 +185,11 @@ int sfh_transform_points_bwd(const float* trans, int Bt, const float* points, co
 int sfh_reproj_loss(const float* inputs, const float* targets, const float* nonzeros,
                     const float* num_nonzero, int B, int N, float* R_b,
                     const float* grad_Rb, float* dinputs, void* stream);
+
+/* Diagnostic: exhaustively compares the kernels' fast correctly-rounded reciprocal with IEEE
+ * rcp.rn over every fp32 value with |z| in (1e-8, 1e37) (the range it is used on; the warp path
+ * falls back to rcp.rn outside).  *mismatches (device uint64, pre-zeroed) receives the count. */
+int sfh_selftest_rcp(unsigned long long* mismatches, void* stream);
 
 #ifdef __cplusplus
 }

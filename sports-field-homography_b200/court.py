@@ -113,8 +113,8 @@ class CourtTemplate:
             return
         fmt = _lib.TMPL_Q2 if len(pal) <= 4 else _lib.TMPL_Q4
         dt = torch.uint8 if fmt == _lib.TMPL_Q2 else torch.int16
-        pitch = (self.Wc + 1 + 15) // 16 * 16
-        packed = torch.zeros((self.Hc + 1, pitch), dtype=dt, device=self.device)
+        pitch = (self.Wc + 2 + 15) // 16 * 16
+        packed = torch.zeros((self.Hc + 2, pitch), dtype=dt, device=self.device)
         err = torch.zeros(1, dtype=torch.int32, device=self.device)
         host_pal = (C.c_float * len(pal))(*pal)
         with torch.cuda.device(self.device):

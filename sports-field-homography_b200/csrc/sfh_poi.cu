@@ -98,6 +98,18 @@ __global__ void __launch_bounds__(32) k_reproj(const float* in, const float* tg,
     if (lane == 0 && Rb) Rb[b] = (float)loss;
 }
 
+__global__ void k_selftest_rcp(unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
+        const float z = __uint_as_float((unsigned)i);
+        const float az = fabsf(z);
+        if (!(az > kEps) || !(az < 1e37f)) continue;
+        if (__float_as_uint(rcp_rn_normal(z)) != __float_as_uint(__frcp_rn(z))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace sfh
 
 using namespace sfh;
@@ -146,6 +158,12 @@ int sfh_reproj_loss(const float* inputs, const float* targets, const float* nonz
     if (!inputs || !targets || !nonzeros || !num_nonzero || B <= 0 || N <= 0) return SFH_E_BADARG;
     if (dinputs && !grad_Rb) return SFH_E_BADARG;
     k_reproj<<<B, 32, 0, (cudaStream_t)stream>>>(inputs, targets, nonzeros, num_nonzero, N, R_b, grad_Rb, dinputs);
+    return (int)cudaGetLastError();
+}
+
+int sfh_selftest_rcp(unsigned long long* mismatches, void* stream) {
+    if (!mismatches) return SFH_E_BADARG;
+    k_selftest_rcp<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(mismatches);
     return (int)cudaGetLastError();
 }
 

@@ -12,6 +12,8 @@
 // owns rows {w, w+8} of a 128x16 tile.  The sampling grid lives in registers only.  Per-sample
 // sums (loss, 9 dtheta terms, score) go lane -> warp shuffle -> smem -> one partial per CTA; the
 // last CTA of a sample (ticket counter, no data atomics) adds the partials in fixed order in fp64.
+#include <stdlib.h>
+#include <string.h>
 #include "sfh_device.cuh"
 #include "sfh_poi.cuh"
 
@@ -23,7 +25,8 @@ struct FusedParams {
     const float* ys;
     sfh_template t;
     int B, H, W;
-    int tiles_x, ntiles;
+    int rows_per_warp;   // R: a CTA covers 128 x 8R output pixels, warp w owns rows w, w+8, ...
+    int ntiles;          // CTAs per sample
     int vec4;            // W % 4 == 0 and all row bases 16-byte aligned
     // kEpiStore / kEpiBwd
     float* out_f;        // [B,C,H,W]
@@ -43,13 +46,12 @@ struct FusedParams {
     float* loss_out;      // scalar, nullable: enables the combine stage
     float* dtheta_total;  // [B,9]
     double* contrib;      // workspace [B]
-    int arrivals;         // CTAs taking a ticket per sample
     // kEpiPredict
     const float* logits;
     int lh, lw, ratio;   // ratio: 1 (same size), 2 (H=2h, W=2w), 0 (score not fused)
     int32_t* out_i;
     float* score;
-    // POI tail block (blockIdx.x == ntiles)
+    // POI work, done by the first warp of tile 0 of every sample
     PoiParams poi;
     // workspace
     int* counters;
@@ -59,7 +61,6 @@ struct FusedParams {
 // Geometry of one output pixel, everything the epilogues need.
 struct Pix {
     Flow f;
-    float ix, iy;
     float ex, wx, sy, ny;   // bilinear factors: ex = x1-ix, wx = ix-x0, sy = y1-iy, ny = iy-y0
     int x0, y0;
 };
@@ -69,35 +70,36 @@ __device__ __forceinline__ Pix pixel_geom(const Homog& Hm, float pu0, float pu3,
                                           float Wc_f, float Hc_f) {
     Pix p;
     p.f = flow_at(Hm, pu0, pu3, pu6, v);
-    p.ix = unnormalize(p.f.x, Wc_f);
-    p.iy = unnormalize(p.f.y, Hc_f);
+    const float ix = unnormalize(p.f.x, Wc_f);
+    const float iy = unnormalize(p.f.y, Hc_f);
     if (MODE == SFH_MODE_NEAREST) {
-        p.x0 = __float2int_rn(p.ix);   // nearbyint: half to even
-        p.y0 = __float2int_rn(p.iy);
+        p.x0 = __float2int_rn(ix);   // nearbyint: half to even
+        p.y0 = __float2int_rn(iy);
         p.ex = p.wx = p.sy = p.ny = 0.f;
     } else {
-        const float fx = floorf(p.ix), fy = floorf(p.iy);
+        const float fx = floorf(ix), fy = floorf(iy);
         p.x0 = (int)fx;
         p.y0 = (int)fy;
-        p.ex = __fsub_rn(__fadd_rn(fx, 1.0f), p.ix);
-        p.wx = __fsub_rn(p.ix, fx);
-        p.sy = __fsub_rn(__fadd_rn(fy, 1.0f), p.iy);
-        p.ny = __fsub_rn(p.iy, fy);
+        // ATen computes (x0+1)-ix and ix-x0; both are exact in fp32, and so is 1-(ix-x0)
+        p.wx = __fsub_rn(ix, fx);
+        p.ex = __fsub_rn(1.0f, p.wx);
+        p.ny = __fsub_rn(iy, fy);
+        p.sy = __fsub_rn(1.0f, p.ny);
     }
     return p;
 }
 
 // ATen accumulation order: nw, ne, sw, se, each step one FMA.
-__device__ __forceinline__ float bilerp(const Pix& p, float a, float b, float c, float d) {
-    float o = __fmul_rn(a, __fmul_rn(p.ex, p.sy));
-    o = __fmaf_rn(b, __fmul_rn(p.wx, p.sy), o);
-    o = __fmaf_rn(c, __fmul_rn(p.ex, p.ny), o);
-    o = __fmaf_rn(d, __fmul_rn(p.wx, p.ny), o);
+__device__ __forceinline__ float bilerp(const Pix& p, const TapVals& t) {
+    float o = __fmul_rn(t.a, __fmul_rn(p.ex, p.sy));
+    o = __fmaf_rn(t.b, __fmul_rn(p.wx, p.sy), o);
+    o = __fmaf_rn(t.c, __fmul_rn(p.ex, p.ny), o);
+    o = __fmaf_rn(t.d, __fmul_rn(p.wx, p.ny), o);
     return o;
 }
 
-// d(out)/d(theta) contribution of one pixel given g = dL/d(out) (already summed over channels
-// into gix/giy):  grid_sampler_2d_backward -> scale*p backward -> bmm backward.
+// d(out)/d(theta) contribution of one pixel given g = dL/d(out):
+// grid_sampler_2d_backward -> scale*p backward -> bmm backward.
 struct GradAcc {
     float xu, x1, yu, y1, zu, z1;    // sums of gX*u, gX, gY*u, gY, gZ*u, gZ over the current row
     float a[9];                      // running dtheta
@@ -122,11 +124,18 @@ struct GradAcc {
     }
 };
 
-// log-sum-exp cross entropy of one pixel, nc logits strided by `cs`.
+// log-sum-exp cross entropy of one pixel, nc logits strided by `cs` (F.cross_entropy, reduction none).
 __device__ __forceinline__ float ce_pixel(const float* lg, size_t cs, int nc, int cls) {
+    if (nc == 4) {
+        const float l0 = __ldcs(lg), l1 = __ldcs(lg + cs), l2 = __ldcs(lg + 2 * cs), l3 = __ldcs(lg + 3 * cs);
+        const float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
+        const float se = expf(l0 - mx) + expf(l1 - mx) + expf(l2 - mx) + expf(l3 - mx);
+        const float sel = cls == 0 ? l0 : cls == 1 ? l1 : cls == 2 ? l2 : l3;
+        return (logf(se) + mx) - sel;
+    }
     float mx = -INFINITY, sel = 0.f;
     for (int c = 0; c < nc; ++c) {
-        const float v = __ldcs(lg + c * cs);
+        const float v = __ldg(lg + c * cs);
         mx = fmaxf(mx, v);
         if (c == cls) sel = v;
     }
@@ -135,33 +144,53 @@ __device__ __forceinline__ float ce_pixel(const float* lg, size_t cs, int nc, in
     return (logf(se) + mx) - sel;
 }
 
+struct Gt4 { longlong2 lo, hi; };
+
+__device__ __forceinline__ Gt4 load_gt(const long long* gt, size_t rowbase, int col, int W, bool full) {
+    Gt4 g;
+    if (full) {
+        g.lo = __ldcs((const longlong2*)(gt + rowbase));
+        g.hi = __ldcs((const longlong2*)(gt + rowbase) + 1);
+    } else {
+        g.lo.x = (col + 0 < W) ? __ldcs(gt + rowbase + 0) : 0;
+        g.lo.y = (col + 1 < W) ? __ldcs(gt + rowbase + 1) : 0;
+        g.hi.x = (col + 2 < W) ? __ldcs(gt + rowbase + 2) : 0;
+        g.hi.y = (col + 3 < W) ? __ldcs(gt + rowbase + 3) : 0;
+    }
+    return g;
+}
+
+#ifndef SFH_MINCTAS_HEAVY
+#define SFH_MINCTAS_HEAVY 3   // loss / backward epilogues: <= 80 registers
+#endif
+#ifndef SFH_MINCTAS_LIGHT
+#define SFH_MINCTAS_LIGHT 4   // store / predict epilogues: <= 64 registers
+#endif
+constexpr int min_ctas(int epi) { return (epi == kEpiStore || epi == kEpiPredict) ? SFH_MINCTAS_LIGHT : SFH_MINCTAS_HEAVY; }
+
 template <int FMT, int MODE, int EPI>
-__global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ FusedParams p) {
-    __shared__ float s_pal[16];
+__global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_constant__ FusedParams p) {
+    __shared__ __align__(16) float s_tab[Taps<FMT>::kSmemFloats];
     __shared__ float s_red[kWarps][kNPart];
     __shared__ double s_fin[kNPart][kFinGroup];
     __shared__ int s_last;
 
-    const int b = blockIdx.y, tile = blockIdx.x;
+    const int b = blockIdx.z, tx = blockIdx.x, ty = blockIdx.y;
+    const int tile = ty * gridDim.x + tx;
     const int H = p.H, W = p.W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool poi_blk = (EPI == kEpiLoss || EPI == kEpiPredict) && tile == p.ntiles;
-    if (poi_blk) {                       // POI tail CTA: first warp does the 52/33 points in fp64
-        poi_block(p.poi, b);
-        if (EPI != kEpiLoss) return;     // in the training pass it also takes a ticket below
-    } else {
-    if (FMT != SFH_TMPL_F32) {
-        if (threadIdx.x < 16) s_pal[threadIdx.x] = p.t.palette[threadIdx.x];
-        __syncthreads();
-    }
-    const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+
+    Taps<FMT> taps;
+    taps.build_tables(p.t, s_tab);
+    if ((EPI == kEpiLoss || EPI == kEpiPredict) && tile == 0 && p.poi.court_poi)
+        poi_block(p.poi, b);                 // first warp: the 52/33 court points in fp64
+    __syncthreads();
+    taps.init(p.t, b, s_tab);
+
     const int col = tx * kTileW + lane * 4;
     const int C = (FMT == SFH_TMPL_F32) ? p.t.channels : 1;
-
     Homog Hm;
     Hm.load(p.theta + 9 * b);
-    Taps<FMT> taps;
-    taps.init(p.t, b, s_pal);
     const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
     const float halfWc = 0.5f * Wc_f, halfHc = 0.5f * Hc_f;
 
@@ -180,31 +209,31 @@ __global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ Fuse
     acc.zero();
     float loss_sum = 0.f, score_sum = 0.f;
 
+    const int R = p.rows_per_warp;
+    const int row0 = ty * (kWarps * R) + warp;
+    const bool full = p.vec4 && (col + 3 < W);
+    const float gscale = (p.kind == SFH_LOSS_MSE ? 2.0f : 1.0f) * p.invN;
+
+    Gt4 gnext;
+    if (EPI == kEpiLoss && row0 < H) gnext = load_gt(p.gt, ((size_t)b * H + row0) * W + col, col, W, full);
+
 #pragma unroll 1
-    for (int rr = 0; rr < kTileH / kWarps; ++rr) {
-        const int row = ty * kTileH + rr * kWarps + warp;
-        if (row >= H) continue;   // warp-uniform; lanes past W stay active (predicated)
+    for (int rr = 0; rr < R; ++rr) {
+        const int row = row0 + rr * kWarps;
+        if (row >= H) break;                 // warp-uniform; lanes past W stay active (predicated)
         const float v = p.ys ? __ldg(p.ys + row) : mesh_coord(row, H);
         const size_t rowbase = ((size_t)b * H + row) * W + col;   // C == 1 offset
-        const bool full = p.vec4 && (col + 3 < W);
 
-        // ---- issue the streaming loads of this row first (latency overlaps the geometry) ----
+        // ---- software pipeline: this row's gt was requested one iteration ago; request the next ----
         float tgt[4];
         if (EPI == kEpiLoss) {
-            long long g[4];
-            if (full) {
-                const longlong2 g01 = __ldcs((const longlong2*)(p.gt + rowbase));
-                const longlong2 g23 = __ldcs((const longlong2*)(p.gt + rowbase) + 1);
-                g[0] = g01.x; g[1] = g01.y; g[2] = g23.x; g[3] = g23.y;
-            } else {
+            const Gt4 g = gnext;
+            if (rr + 1 < R && row + kWarps < H)
+                gnext = load_gt(p.gt, rowbase + (size_t)kWarps * W, col, W, full);
+            const float gf[4] = {(float)(int)g.lo.x, (float)(int)g.lo.y, (float)(int)g.hi.x, (float)(int)g.hi.y};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) g[j] = (col + j < W) ? __ldcs(p.gt + rowbase + j) : 0;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float gf = (float)(int)g[j];   // class ids: low 32 bits carry the value
-                tgt[j] = p.nc_pow2 ? __fmul_rn(gf, p.inv_nc) : __fdiv_rn(gf, (float)p.nc);
-            }
+            for (int j = 0; j < 4; ++j)      // class ids: the low 32 bits carry the value
+                tgt[j] = p.nc_pow2 ? __fmul_rn(gf[j], p.inv_nc) : __fdiv_rn(gf[j], (float)p.nc);
         }
 
         Pix px[4];
@@ -230,18 +259,17 @@ __global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ Fuse
                     if (MODE == SFH_MODE_NEAREST) {
                         o[j] = taps.fetch1(c, px[j].x0, px[j].y0);
                     } else {
-                        float ta, tb, tc, td;
-                        taps.fetch4(c, px[j].x0, px[j].y0, ta, tb, tc, td);
-                        if (EPI == kEpiStore) o[j] = bilerp(px[j], ta, tb, tc, td);
+                        const TapVals t = taps.fetch4(c, px[j].x0, px[j].y0);
+                        if (EPI == kEpiStore) o[j] = bilerp(px[j], t);
                         if (EPI == kEpiBwd) {
-                            gix[j] += ((tb - ta) * px[j].sy + (td - tc) * px[j].ny) * go[j];
-                            giy[j] += ((tc - ta) * px[j].ex + (td - tb) * px[j].wx) * go[j];
+                            gix[j] += ((t.b - t.a) * px[j].sy + (t.d - t.c) * px[j].ny) * go[j];
+                            giy[j] += ((t.c - t.a) * px[j].ex + (t.d - t.b) * px[j].wx) * go[j];
                         }
                     }
                 }
                 if (EPI == kEpiStore) {
                     if (full) {
-                        st_stream((float4*)(p.out_f + off), make_float4(o[0], o[1], o[2], o[3]));
+                        __stcs((float4*)(p.out_f + off), make_float4(o[0], o[1], o[2], o[3]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) if (col + j < W) p.out_f[off + j] = o[j];
@@ -258,17 +286,17 @@ __global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ Fuse
 
         if (EPI == kEpiLoss) {
             float o[4];
+            TapVals t[4];
             bool any_edge = false;
-            float ta[4], tb[4], tc[4], td[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                taps.fetch4(0, px[j].x0, px[j].y0, ta[j], tb[j], tc[j], td[j]);
-                o[j] = bilerp(px[j], ta[j], tb[j], tc[j], td[j]);
-                any_edge |= (ta[j] != tb[j]) | (tc[j] != td[j]) | (ta[j] != tc[j]);
+                t[j] = taps.fetch4(0, px[j].x0, px[j].y0);
+                o[j] = bilerp(px[j], t[j]);
+                any_edge |= !t[j].uni;
             }
             if (p.out_f) {
                 if (full) {
-                    st_stream((float4*)(p.out_f + rowbase), make_float4(o[0], o[1], o[2], o[3]));
+                    __stcs((float4*)(p.out_f + rowbase), make_float4(o[0], o[1], o[2], o[3]));
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) if (col + j < W) p.out_f[rowbase + j] = o[j];
@@ -279,20 +307,22 @@ __global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ Fuse
             for (int j = 0; j < 4; ++j) {
                 const float d = o[j] - tgt[j];
                 float l;
-                if (p.kind == SFH_LOSS_MSE) { l = d * d; g[j] = 2.0f * d; }
-                else if (fabsf(d) < 1.0f)   { l = 0.5f * d * d; g[j] = d; }
-                else                        { l = fabsf(d) - 0.5f; g[j] = d > 0.f ? 1.0f : -1.0f; }
+                if (p.kind == SFH_LOSS_MSE || fabsf(d) < 1.0f) {   // MSE d^2 ; SmoothL1(beta=1) 0.5 d^2
+                    l = d * d; g[j] = d;
+                } else {
+                    l = 2.0f * fabsf(d) - 1.0f; g[j] = d > 0.f ? 1.0f : -1.0f;   // doubled, halved below
+                }
                 if (col + j >= W) { l = 0.f; g[j] = 0.f; }
                 loss_sum += l;
-                g[j] *= p.invN;
+                g[j] *= gscale;
             }
             // the gradient lives on footprints that straddle a class edge; a uniform footprint
             // cancels exactly (a*sy - a*sy), so whole warps skip the chain rule when none is on one
             if (__any_sync(0xffffffffu, any_edge)) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float gix = ((tb[j] - ta[j]) * px[j].sy + (td[j] - tc[j]) * px[j].ny) * g[j];
-                    const float giy = ((tc[j] - ta[j]) * px[j].ex + (td[j] - tb[j]) * px[j].wx) * g[j];
+                    const float gix = ((t[j].b - t[j].a) * px[j].sy + (t[j].d - t[j].c) * px[j].ny) * g[j];
+                    const float giy = ((t[j].c - t[j].a) * px[j].ex + (t[j].d - t[j].b) * px[j].wx) * g[j];
                     acc.add(px[j], gix, giy, halfWc, halfHc, u[j]);
                 }
                 acc.end_row(v);
@@ -304,17 +334,12 @@ __global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ Fuse
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float o;
-                if (MODE == SFH_MODE_NEAREST) {
-                    o = taps.fetch1(0, px[j].x0, px[j].y0);
-                } else {
-                    float ta, tb, tc, td;
-                    taps.fetch4(0, px[j].x0, px[j].y0, ta, tb, tc, td);
-                    o = bilerp(px[j], ta, tb, tc, td);
-                }
+                if (MODE == SFH_MODE_NEAREST) o = taps.fetch1(0, px[j].x0, px[j].y0);
+                else o = bilerp(px[j], taps.fetch4(0, px[j].x0, px[j].y0));
                 cls[j] = __float2int_rz(__fmul_rn(o, (float)p.nc));   // (warp*nc).int()
             }
             if (full) {
-                st_stream((int4*)(p.out_i + rowbase), make_int4(cls[0], cls[1], cls[2], cls[3]));
+                __stcs((int4*)(p.out_i + rowbase), make_int4(cls[0], cls[1], cls[2], cls[3]));
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) if (col + j < W) p.out_i[rowbase + j] = cls[j];
@@ -339,6 +364,7 @@ __global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ Fuse
     if (EPI == kEpiPredict && !(p.score && p.ratio != 0)) return;
 
     // ---------------- per-sample reduction: lane -> warp -> CTA partial -> last CTA -----------
+    if (EPI == kEpiLoss && p.kind != SFH_LOSS_MSE) loss_sum *= 0.5f;
     float vals[kNPart];
     vals[0] = loss_sum;
 #pragma unroll
@@ -354,24 +380,17 @@ __global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ Fuse
         if (lane == 0) s_red[warp][k] = s;
     }
     __syncthreads();
-    float* part = p.partials + ((size_t)b * p.ntiles + tile) * kNPart;
     if (threadIdx.x < kNPart) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) s += s_red[w][threadIdx.x];
-        part[threadIdx.x] = s;
+        __stcg(p.partials + ((size_t)b * p.ntiles + tile) * kNPart + threadIdx.x, s);
     }
-    }   // !poi_blk
-
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const int prev = atomicAdd(p.counters + b, 1);   // ticket only; no data goes through atomics
-        s_last = (prev == p.arrivals - 1);
-    }
+    if (threadIdx.x == 0) s_last = (ticket_release(p.counters + b) == p.ntiles - 1);
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
+    __threadfence();   // acquire side, once per sample
     {
         const int k = threadIdx.x / kFinGroup, jj = threadIdx.x % kFinGroup;
         if (k < kNPart) {
@@ -422,9 +441,8 @@ __global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ Fuse
             int last2 = 0;
             if (lane == 0) {
                 const double Rv = rep ? (double)__ldcg(p.poi.Rb + b) : 0.0;
-                p.contrib[b] = cr * s_fin[0][0] + cp * Rv;
-                __threadfence();
-                last2 = (atomicAdd(p.counters + B, 1) == B - 1);
+                __stcg(p.contrib + b, cr * s_fin[0][0] + cp * Rv);
+                last2 = (ticket_release(p.counters + B) == B - 1);
             }
             last2 = __shfl_sync(0xffffffffu, last2, 0);
             if (last2) {                    // last sample of the batch: fixed-order sum over b
@@ -470,9 +488,9 @@ __global__ void __launch_bounds__(kThreads) k_consistency_generic(const int32_t*
 template <int BITS, typename T>
 __global__ void k_pack(const float* tmpl, int Hc, int Wc, T* q, int pitch, int npal,
                        const __grid_constant__ sfh_template pal, int32_t* err) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // packed column 0..Wc
-    const int j = blockIdx.y;                               // packed row    0..Hc
-    if (i > Wc) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // packed column 0..Wc+1 (last one all zero)
+    const int j = blockIdx.y;                               // packed row    0..Hc+1 (last one all zero)
+    if (i > Wc + 1) return;
     unsigned v = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -499,7 +517,7 @@ static int check_template(const sfh_template* t) {
     if (!t || !t->data || t->height <= 0 || t->width <= 0) return SFH_E_BADARG;
     if (t->fmt == SFH_TMPL_F32) return t->channels >= 1 ? 0 : SFH_E_BADARG;
     if (t->fmt == SFH_TMPL_Q2 || t->fmt == SFH_TMPL_Q4) {
-        if (t->channels != 1 || t->pitch < t->width + 1) return SFH_E_BADARG;
+        if (t->channels != 1 || t->pitch < t->width + 2) return SFH_E_BADARG;
         if (t->n_palette < 1 || t->n_palette > (t->fmt == SFH_TMPL_Q2 ? 4 : 16)) return SFH_E_BADARG;
         if (t->palette[0] != 0.0f) return SFH_E_BADARG;
         return 0;
@@ -512,8 +530,16 @@ static void fill_common(FusedParams& p, const float* theta, const sfh_template* 
     memset(&p, 0, sizeof(p));
     p.theta = theta; p.xs = xs; p.ys = ys; p.t = *t;
     p.B = B; p.H = H; p.W = W;
-    p.tiles_x = (W + kTileW - 1) / kTileW;
-    p.ntiles = p.tiles_x * ((H + kTileH - 1) / kTileH);
+    // rows per warp: the largest R in {16,8,4,2,1} that still leaves >= 8 waves of CTAs
+    // (3 CTAs/SM x 148 SMs); bigger tiles amortise the per-CTA prologue and reduction.
+    static const int forced = [] { const char* e = getenv("SFH_ROWS_PER_WARP"); return e ? atoi(e) : 0; }();
+    const int tiles_x = (W + kTileW - 1) / kTileW;
+    int R = 16;
+    if (forced > 0) R = forced;
+    else
+        while (R > 1 && (int64_t)tiles_x * ((H + kWarps * R - 1) / (kWarps * R)) * B < 8 * 3 * 148) R >>= 1;
+    p.rows_per_warp = R;
+    p.ntiles = tiles_x * ((H + kWarps * R - 1) / (kWarps * R));
 }
 
 static inline bool aligned16(const void* q) { return ((uintptr_t)q & 15u) == 0; }
@@ -524,13 +550,14 @@ static int setup_ws(FusedParams& p, void* ws, int64_t ws_bytes) {
     p.counters = (int*)ws;                                             // [B+1]
     p.contrib = (double*)((char*)ws + align_up((int64_t)(p.B + 1) * 4, 256));   // [B]
     p.partials = (float*)((char*)p.contrib + align_up((int64_t)p.B * 8, 256));
-    p.arrivals = p.ntiles;
     return 0;
 }
 
 template <int MODE, int EPI>
-static int launch_fused(const FusedParams& p, bool poi_tail, cudaStream_t st) {
-    dim3 grid(p.ntiles + (poi_tail ? 1 : 0), p.B), block(kThreads);
+static int launch_fused(const FusedParams& p, cudaStream_t st) {
+    if (p.B > 65535) return SFH_E_BADARG;
+    const int tiles_x = (p.W + kTileW - 1) / kTileW;
+    dim3 grid(tiles_x, p.ntiles / tiles_x, p.B), block(kThreads);
     switch (p.t.fmt) {
         case SFH_TMPL_F32: k_fused<SFH_TMPL_F32, MODE, EPI><<<grid, block, 0, st>>>(p); break;
         case SFH_TMPL_Q2:  k_fused<SFH_TMPL_Q2, MODE, EPI><<<grid, block, 0, st>>>(p); break;
@@ -549,7 +576,7 @@ extern "C" {
 int sfh_abi_version(void) { return SFH_ABI_VERSION; }
 
 const char* sfh_build_info(void) {
-    return "sfh_b200 abi " "1" " sm_100a tile 128x16 threads 256 (" __DATE__ " " __TIME__ ")";
+    return "sfh_b200 abi " "1" " sm_100a tile 128x(8R) threads 256 (" __DATE__ " " __TIME__ ")";
 }
 
 const char* sfh_error_string(int code) {
@@ -566,20 +593,20 @@ const char* sfh_error_string(int code) {
 
 int64_t sfh_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
-    const int64_t ntiles = (int64_t)((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+    const int64_t ntiles = (int64_t)((W + kTileW - 1) / kTileW) * ((H + kWarps - 1) / kWarps);   // R = 1 upper bound
     return align_up((int64_t)(B + 1) * 4, 256) + align_up((int64_t)B * 8, 256) + (int64_t)B * ntiles * kNPart * 4;
 }
 
 int sfh_template_pack(const float* tmpl, int Hc, int Wc, const float* palette_host, int n_palette,
                       void* packed, int pitch, int fmt, int32_t* err_flag, void* stream) {
-    if (!tmpl || !packed || !palette_host || !err_flag || Hc <= 0 || Wc <= 0 || pitch < Wc + 1) return SFH_E_BADARG;
+    if (!tmpl || !packed || !palette_host || !err_flag || Hc <= 0 || Wc <= 0 || pitch < Wc + 2) return SFH_E_BADARG;
     const int cap = fmt == SFH_TMPL_Q2 ? 4 : fmt == SFH_TMPL_Q4 ? 16 : 0;
     if (!cap) return SFH_E_BADFMT;
     if (n_palette < 1 || n_palette > cap || palette_host[0] != 0.0f) return SFH_E_BADARG;
     sfh_template pal;
     memset(&pal, 0, sizeof(pal));
     for (int i = 0; i < n_palette; ++i) pal.palette[i] = palette_host[i];
-    dim3 block(128), grid((Wc + 1 + 127) / 128, Hc + 1);
+    dim3 block(128), grid((Wc + 2 + 127) / 128, Hc + 2);
     cudaStream_t st = (cudaStream_t)stream;
     if (fmt == SFH_TMPL_Q2) k_pack<2, uint8_t><<<grid, block, 0, st>>>(tmpl, Hc, Wc, (uint8_t*)packed, pitch, n_palette, pal, err_flag);
     else                    k_pack<4, uint16_t><<<grid, block, 0, st>>>(tmpl, Hc, Wc, (uint16_t*)packed, pitch, n_palette, pal, err_flag);
@@ -596,8 +623,8 @@ int sfh_warp_fwd(const float* theta, const sfh_template* tmpl, const float* xs, 
     p.out_f = out;
     p.vec4 = (W % 4 == 0) && aligned16(out);
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == SFH_MODE_BILINEAR) return launch_fused<SFH_MODE_BILINEAR, kEpiStore>(p, false, st);
-    if (mode == SFH_MODE_NEAREST) return launch_fused<SFH_MODE_NEAREST, kEpiStore>(p, false, st);
+    if (mode == SFH_MODE_BILINEAR) return launch_fused<SFH_MODE_BILINEAR, kEpiStore>(p, st);
+    if (mode == SFH_MODE_NEAREST) return launch_fused<SFH_MODE_NEAREST, kEpiStore>(p, st);
     return SFH_E_BADMODE;
 }
 
@@ -612,7 +639,7 @@ int sfh_warp_bwd(const float* theta, const sfh_template* tmpl, const float* xs, 
     if ((rc = setup_ws(p, workspace, workspace_bytes))) return rc;
     p.grad_out = grad_out; p.dtheta = dtheta;
     p.vec4 = (W % 4 == 0) && aligned16(grad_out);
-    return launch_fused<SFH_MODE_BILINEAR, kEpiBwd>(p, false, (cudaStream_t)stream);
+    return launch_fused<SFH_MODE_BILINEAR, kEpiBwd>(p, (cudaStream_t)stream);
 }
 
 int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* a, void* stream) {
@@ -640,12 +667,11 @@ int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* a
         p.poi.N = a->N; p.poi.normalize = 1; p.poi.poi_out = a->poi_out;
         p.poi.gt_poi = a->gt_poi; p.poi.nonzeros = a->nonzeros; p.poi.num_nonzero = a->num_nonzero;
         p.poi.Rb = a->R_b; p.poi.K = a->dRb_dtheta;
-        p.arrivals = p.ntiles + 1;
     }
     p.weights = a->weights; p.w_f64 = a->weights_f64; p.w_outer = a->weights_outer;
     p.rec_lambda = a->rec_lambda; p.reproj_lambda = a->reproj_lambda;
     p.loss_out = a->loss_out; p.dtheta_total = a->dtheta_total;
-    return launch_fused<SFH_MODE_BILINEAR, kEpiLoss>(p, poi_tail, (cudaStream_t)stream);
+    return launch_fused<SFH_MODE_BILINEAR, kEpiLoss>(p, (cudaStream_t)stream);
 }
 
 int sfh_predict_tail(const sfh_template* tmpl, const sfh_predict_tail_args* a, void* stream) {
@@ -670,8 +696,8 @@ int sfh_predict_tail(const sfh_template* tmpl, const sfh_predict_tail_args* a, v
         p.poi.N = a->N; p.poi.normalize = 1; p.poi.poi_out = a->poi_out;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (a->mode == SFH_MODE_NEAREST) rc = launch_fused<SFH_MODE_NEAREST, kEpiPredict>(p, poi_tail, st);
-    else if (a->mode == SFH_MODE_BILINEAR) rc = launch_fused<SFH_MODE_BILINEAR, kEpiPredict>(p, poi_tail, st);
+    if (a->mode == SFH_MODE_NEAREST) rc = launch_fused<SFH_MODE_NEAREST, kEpiPredict>(p, st);
+    else if (a->mode == SFH_MODE_BILINEAR) rc = launch_fused<SFH_MODE_BILINEAR, kEpiPredict>(p, st);
     else return SFH_E_BADMODE;
     if (rc) return rc;
     if (a->score && p.ratio == 0) {

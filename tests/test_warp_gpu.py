@@ -56,6 +56,15 @@ def test_native_library_is_loaded():
     assert torch.cuda.get_device_capability(0)[0] == 10
 
 
+def test_fast_reciprocal_is_correctly_rounded_everywhere_it_is_used():
+    """1/Z must be IEEE-exact for the coordinates to match the reference bit for bit: compare the
+    kernels' MUFU.RCP + FMA reciprocal with rcp.rn over ALL fp32 inputs with |z| in (1e-8, 1e37)."""
+    bad = torch.zeros(1, dtype=torch.int64, device=DEV)
+    rc = sfh_b200._lib.lib().sfh_selftest_rcp(bad.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    sfh_b200._lib.check(rc, "sfh_selftest_rcp")
+    assert int(bad.item()) == 0
+
+
 # ------------------------------------------------------------------------------ golden vectors
 def test_golden_small_all_outputs(golden_small):
     g = golden_small
