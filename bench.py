@@ -310,7 +310,8 @@ def time_workload(wl, steps, warmup, use_graph, dist_vec=None):
         n = min(steps, 200)
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         for i, (a, b) in enumerate(evs):
-            a.record()
+            torch.cuda._sleep(400000)   # GPU stays busy while the CPU queues a / launch / b, so the pair
+            a.record()                  # brackets only the kernel, not Python's launch latency
             wl.step(i)
             b.record()
         torch.cuda.synchronize()

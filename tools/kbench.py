@@ -32,7 +32,8 @@ def run(tag, fn, nbytes):
     torch.cuda.synchronize()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.n)]
     for i, (e0, e1) in enumerate(evs):
-        e0.record()
+        torch.cuda._sleep(400000)      # keep the GPU busy while the CPU queues e0 / launch / e1, so the
+        e0.record()                    # pair brackets only the kernel, not Python's launch latency
         fn(i)
         e1.record()
     torch.cuda.synchronize()
