@@ -61,6 +61,14 @@ typedef struct sfh_template {
     int32_t     n_palette;   /* Q2/Q4: number of valid palette entries */
     int64_t     batch_stride;/* F32: elements between consecutive samples, 0 = one shared template */
     float       palette[16]; /* Q2/Q4: texel value of each palette index */
+    /* Q2/Q4, optional: summed-area table of "packed entry straddles a class edge",
+     * S[(j+1)*sat_pitch + (i+1)] = #{edge entries (j',i') : j' <= j, i' <= i}, row 0 / column 0
+     * zero, (Hc+3) x sat_pitch uint32.  With it, 16x8 output patches whose sampling footprint
+     * contains no class edge are written as a constant (nearest: bit-exact; bilinear: within
+     * 2 ulp of the interpolated constant, and the exactly-zero gradient is kept).  NULL disables
+     * the shortcut: every pixel is then evaluated in ATen's exact operation order. */
+    const uint32_t* sat;
+    int32_t     sat_pitch;
 } sfh_template;
 
 int sfh_abi_version(void);
@@ -72,11 +80,13 @@ const char* sfh_error_string(int code);
 int64_t sfh_workspace_bytes(int B, int H, int W);
 
 /* Pack a class-index template (fp32 [Hc,Wc], every texel equal to one of palette[0..n)) into
- * the Q2 (n<=4) or Q4 (n<=16) layout.  *err_flag (device int32, pre-zeroed) is set to 1 if a
+ * the Q2 (n<=4) or Q4 (n<=16) layout and, optionally, its edge summed-area table.  *err_flag (device int32, pre-zeroed) is set to 1 if a
  * texel matches no palette entry.  Replaces nothing in the reference: it is the "stage the
  * template once" step; source data is open_court_template's tensor (utils/dataset.py:47-61). */
 int sfh_template_pack(const float* tmpl, int Hc, int Wc, const float* palette_host, int n_palette,
-                      void* packed, int pitch, int fmt, int32_t* err_flag, void* stream);
+                      void* packed, int pitch, int fmt, int32_t* err_flag,
+                      uint32_t* sat /* nullable, zero-filled (Hc+3) x sat_pitch */, int sat_pitch,
+                      void* stream);
 
 /* kornia HomographyWarper.forward(patch_src, src_homo_dst) — models/reconstructor.py:116
  * (Reconstructor.warp, :109-118).  out: [B,C,H,W] fp32. */

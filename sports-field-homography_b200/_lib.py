@@ -27,7 +27,8 @@ class SfhTemplate(C.Structure):
     """struct sfh_template (include/sfh_b200.h)."""
     _fields_ = [("data", C.c_void_p), ("fmt", C.c_int32), ("channels", C.c_int32),
                 ("height", C.c_int32), ("width", C.c_int32), ("pitch", C.c_int32),
-                ("n_palette", C.c_int32), ("batch_stride", C.c_int64), ("palette", C.c_float * 16)]
+                ("n_palette", C.c_int32), ("batch_stride", C.c_int64), ("palette", C.c_float * 16),
+                ("sat", C.c_void_p), ("sat_pitch", C.c_int32)]
 
 
 class SfhTrainTailArgs(C.Structure):
@@ -66,7 +67,7 @@ SIGNATURES = {
     "sfh_build_info": (C.c_char_p, []),
     "sfh_error_string": (C.c_char_p, [_I]),
     "sfh_workspace_bytes": (_L, [_I, _I, _I]),
-    "sfh_template_pack": (_I, [_P, _I, _I, C.POINTER(C.c_float), _I, _P, _I, _I, _P, _P]),
+    "sfh_template_pack": (_I, [_P, _I, _I, C.POINTER(C.c_float), _I, _P, _I, _I, _P, _P, _I, _P]),
     "sfh_warp_fwd": (_I, [_P, _T, _P, _P, _I, _I, _I, _I, _P, _P]),
     "sfh_warp_bwd": (_I, [_P, _T, _P, _P, _P, _I, _I, _I, _P, _P, _L, _P]),
     "sfh_warp_loss_fwd_bwd": (_I, [_T, C.POINTER(SfhTrainTailArgs), _P]),

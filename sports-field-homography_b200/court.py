@@ -92,6 +92,7 @@ class CourtTemplate:
         self.fmt = _lib.TMPL_F32
         self.palette = None
         self.pitch = 0
+        self.sat, self.sat_pitch = None, 0
         if shared:
             self.f32 = court_img[0:1].contiguous()
             self.batch_stride = 0
@@ -116,17 +117,23 @@ class CourtTemplate:
         pitch = (self.Wc + 2 + 15) // 16 * 16
         packed = torch.zeros((self.Hc + 2, pitch), dtype=dt, device=self.device)
         err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        sat_pitch = (self.Wc + 3 + 3) // 4 * 4
+        sat = torch.zeros((self.Hc + 3, sat_pitch), dtype=torch.int32, device=self.device)
         host_pal = (C.c_float * len(pal))(*pal)
         with torch.cuda.device(self.device):
             rc = _lib.lib().sfh_template_pack(self.f32.data_ptr(), self.Hc, self.Wc, host_pal, len(pal),
                                               packed.data_ptr(), pitch, fmt, err.data_ptr(),
+                                              sat.data_ptr(), sat_pitch,
                                               torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "sfh_template_pack")
         if int(err.item()) != 0:
             raise RuntimeError("sfh_template_pack: template texel not in palette")
         self.fmt, self.palette, self.pitch, self.data = fmt, pal, pitch, packed
+        self.sat, self.sat_pitch = sat, sat_pitch
 
-    def desc(self) -> _lib.SfhTemplate:
+    def desc(self, edge_shortcut: bool = True) -> _lib.SfhTemplate:
+        """ctypes descriptor; ``edge_shortcut=False`` withholds the summed-area table so that every
+        pixel is evaluated in ATen's exact operation order (see include/sfh_b200.h)."""
         d = _lib.SfhTemplate()
         d.data = self.data.data_ptr()
         d.fmt, d.channels, d.height, d.width = self.fmt, self.C, self.Hc, self.Wc
@@ -136,4 +143,6 @@ class CourtTemplate:
             d.n_palette = len(self.palette)
             for i, v in enumerate(self.palette):
                 d.palette[i] = v
+        if edge_shortcut and self.sat is not None:
+            d.sat, d.sat_pitch = self.sat.data_ptr(), self.sat_pitch
         return d

@@ -146,16 +146,16 @@ __device__ __forceinline__ float ce_pixel(const float* lg, size_t cs, int nc, in
 
 struct Gt4 { longlong2 lo, hi; };
 
-__device__ __forceinline__ Gt4 load_gt(const long long* gt, size_t rowbase, int col, int W, bool full) {
+__device__ __forceinline__ Gt4 load_gt(const long long* gt, size_t rowbase, int col, int W, bool vec, bool row_ok) {
     Gt4 g;
-    if (full) {
+    if (vec) {
         g.lo = __ldcs((const longlong2*)(gt + rowbase));
         g.hi = __ldcs((const longlong2*)(gt + rowbase) + 1);
     } else {
-        g.lo.x = (col + 0 < W) ? __ldcs(gt + rowbase + 0) : 0;
-        g.lo.y = (col + 1 < W) ? __ldcs(gt + rowbase + 1) : 0;
-        g.hi.x = (col + 2 < W) ? __ldcs(gt + rowbase + 2) : 0;
-        g.hi.y = (col + 3 < W) ? __ldcs(gt + rowbase + 3) : 0;
+        g.lo.x = (row_ok && col + 0 < W) ? __ldcs(gt + rowbase + 0) : 0;
+        g.lo.y = (row_ok && col + 1 < W) ? __ldcs(gt + rowbase + 1) : 0;
+        g.hi.x = (row_ok && col + 2 < W) ? __ldcs(gt + rowbase + 2) : 0;
+        g.hi.y = (row_ok && col + 3 < W) ? __ldcs(gt + rowbase + 3) : 0;
     }
     return g;
 }
@@ -168,30 +168,99 @@ __device__ __forceinline__ Gt4 load_gt(const long long* gt, size_t rowbase, int 
 #endif
 constexpr int min_ctas(int epi) { return (epi == kEpiStore || epi == kEpiPredict) ? SFH_MINCTAS_LIGHT : SFH_MINCTAS_HEAVY; }
 
+constexpr int kMaxR = 16;        // bands (8 rows each) per CTA
+constexpr int kPatchW = 16;      // a warp owns a 16 x 8 pixel patch per band: lane = (ly 0..7, lx 0..3), 4 px per lane
+constexpr float kBoxMargin = 1.0f / 64.0f;   // slack (in texels) on the patch bounding box, >> fp32 rounding of ix
+
+// ------------------------------------------------------------------------------------------
+// The fused kernel.
+//
+// CTA tile: 128 x 8R output pixels of one sample; 8 warps side by side, each owning a 16-px-wide
+// column strip and walking down R bands of 8 rows.  Per band a lane owns 4 consecutive pixels of
+// one row: 4 lanes cover 64 B (fp32/int32 out) or 128 B (int64 gt) of a row, the 8 warps of the
+// CTA together 512 B / 1 KiB contiguous.
+//
+// Court templates are piecewise-constant class maps, so most 16x8 patches sample one class only.
+// Before the pixel loop the CTA classifies its patches: x(u,v) = X/Z and y(u,v) are monotone in u
+// and in v as long as Z keeps its sign, hence the patch's sampling coordinates are bounded by the
+// values at its 4 corners; a summed-area table of "footprint straddles a class edge" over the
+// packed template answers "any edge inside the bounding box?" with 4 loads.  Edge-free patches
+// store the class value directly (their theta-gradient is exactly zero, as in ATen where the four
+// taps cancel); only patches on class edges run the per-pixel homography + bilinear + chain rule.
+// ------------------------------------------------------------------------------------------
 template <int FMT, int MODE, int EPI>
 __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_constant__ FusedParams p) {
     __shared__ __align__(16) float s_tab[Taps<FMT>::kSmemFloats];
     __shared__ float s_red[kWarps][kNPart];
     __shared__ double s_fin[kNPart][kFinGroup];
+    __shared__ float s_gx[kMaxR + 1][kWarps + 1], s_gy[kMaxR + 1][kWarps + 1], s_gz[kMaxR + 1][kWarps + 1];
+    __shared__ int s_patch[kMaxR][kWarps];   // palette index of an edge-free patch, -1: per-pixel path
     __shared__ int s_last;
 
     const int b = blockIdx.z, tx = blockIdx.x, ty = blockIdx.y;
     const int tile = ty * gridDim.x + tx;
     const int H = p.H, W = p.W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = lane & 3, ly = lane >> 2;
+    const int R = p.rows_per_warp;
+    const int band0 = ty * (8 * R);          // first row of the CTA tile
+    const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
 
     Taps<FMT> taps;
     taps.build_tables(p.t, s_tab);
     if ((EPI == kEpiLoss || EPI == kEpiPredict) && tile == 0 && p.poi.court_poi)
         poi_block(p.poi, b);                 // first warp: the 52/33 court points in fp64
-    __syncthreads();
-    taps.init(p.t, b, s_tab);
-
-    const int col = tx * kTileW + lane * 4;
-    const int C = (FMT == SFH_TMPL_F32) ? p.t.channels : 1;
     Homog Hm;
     Hm.load(p.theta + 9 * b);
-    const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
+
+    const bool classify = (FMT != SFH_TMPL_F32) && (p.t.sat != nullptr);
+    if (classify && threadIdx.x < (kWarps + 1) * (R + 1)) {
+        // sampling coordinates on the (R+1) x 9 grid of patch corners (rows 8r, columns 16k)
+        const int r = threadIdx.x / (kWarps + 1), k = threadIdx.x - r * (kWarps + 1);
+        const int grow = min(band0 + 8 * r, H - 1), gcol = min(tx * kTileW + kPatchW * k, W - 1);
+        const float gu = p.xs ? __ldg(p.xs + gcol) : mesh_coord(gcol, W);
+        const float gv = p.ys ? __ldg(p.ys + grow) : mesh_coord(grow, H);
+        const Flow f = flow_at(Hm, __fmul_rn(gu, Hm.h[0]), __fmul_rn(gu, Hm.h[3]), __fmul_rn(gu, Hm.h[6]), gv);
+        s_gx[r][k] = __fmul_rn(__fmaf_rn(__fadd_rn(f.x, 1.0f), Wc_f, -1.0f), 0.5f);
+        s_gy[r][k] = __fmul_rn(__fmaf_rn(__fadd_rn(f.y, 1.0f), Hc_f, -1.0f), 0.5f);
+        s_gz[r][k] = f.zok ? __fdividef(1.0f, f.s) : __int_as_float(0x7fc00000);   // sign/size of Z; NaN poisons the patch
+    }
+    __syncthreads();
+    taps.init(p.t, b, s_tab);
+    if (classify && threadIdx.x < kWarps * R) {
+        const int r = threadIdx.x / kWarps, k = threadIdx.x % kWarps;
+        const float x00 = s_gx[r][k], x01 = s_gx[r][k + 1], x10 = s_gx[r + 1][k], x11 = s_gx[r + 1][k + 1];
+        const float y00 = s_gy[r][k], y01 = s_gy[r][k + 1], y10 = s_gy[r + 1][k], y11 = s_gy[r + 1][k + 1];
+        const float z00 = s_gz[r][k], z01 = s_gz[r][k + 1], z10 = s_gz[r + 1][k], z11 = s_gz[r + 1][k + 1];
+        const float xmin = fminf(fminf(x00, x01), fminf(x10, x11)), xmax = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11));
+        const float ymin = fminf(fminf(y00, y01), fminf(y10, y11)), ymax = fmaxf(fmaxf(y00, y01), fmaxf(y10, y11));
+        // Z of one sign at the 4 corners (it is affine in (u,v)) => no horizon inside the patch
+        const bool zpos = (z00 > 0.f) & (z01 > 0.f) & (z10 > 0.f) & (z11 > 0.f);
+        const bool zneg = (z00 < 0.f) & (z01 < 0.f) & (z10 < 0.f) & (z11 < 0.f);
+        const bool fin = (x00 == x00) & (x01 == x01) & (x10 == x10) & (x11 == x11) &
+                         (y00 == y00) & (y01 == y01) & (y10 == y10) & (y11 == y11) &
+                         (xmin > -1e9f) & (xmax < 1e9f) & (ymin > -1e9f) & (ymax < 1e9f);
+        int cls = -1;
+        if ((zpos | zneg) & fin) {
+            // packed-template entries any pixel of the patch can touch (bilinear: floor+1,
+            // nearest: rint+1 <= floor+2), clamped onto the all-zero border like the sampler does
+            const int wmax = p.t.width + 1, hmax = p.t.height + 1;
+            const int i0 = min(max(__float2int_rd(xmin - kBoxMargin) + 1, 0), wmax);
+            const int i1 = min(max(__float2int_rd(xmax + kBoxMargin) + 2, 0), wmax);
+            const int j0 = min(max(__float2int_rd(ymin - kBoxMargin) + 1, 0), hmax);
+            const int j1 = min(max(__float2int_rd(ymax + kBoxMargin) + 2, 0), hmax);
+            const unsigned* S = p.t.sat;
+            const int sp = p.t.sat_pitch;
+            const unsigned cnt = __ldg(S + (j1 + 1) * sp + (i1 + 1)) - __ldg(S + j0 * sp + (i1 + 1))
+                               - __ldg(S + (j1 + 1) * sp + i0) + __ldg(S + j0 * sp + i0);
+            if (cnt == 0u) cls = (int)taps.entry_class(i0, j0);
+        }
+        s_patch[r][k] = cls;
+    }
+    __syncthreads();
+
+    const int col = tx * kTileW + warp * kPatchW + lx * 4;
+    const int C = (FMT == SFH_TMPL_F32) ? p.t.channels : 1;
     const float halfWc = 0.5f * Wc_f, halfHc = 0.5f * Hc_f;
 
     // column invariants: u and the first bmm product u*h{0,3,6}
@@ -208,34 +277,89 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     GradAcc acc;
     acc.zero();
     float loss_sum = 0.f, score_sum = 0.f;
-
-    const int R = p.rows_per_warp;
-    const int row0 = ty * (kWarps * R) + warp;
-    const bool full = p.vec4 && (col + 3 < W);
+    const bool colvec = p.vec4 && (col + 3 < W);
     const float gscale = (p.kind == SFH_LOSS_MSE ? 2.0f : 1.0f) * p.invN;
+    const float ncf = (float)p.nc;
 
     Gt4 gnext;
-    if (EPI == kEpiLoss && row0 < H) gnext = load_gt(p.gt, ((size_t)b * H + row0) * W + col, col, W, full);
+    if (EPI == kEpiLoss) {
+        const int r0 = band0 + ly;
+        gnext = load_gt(p.gt, ((size_t)b * H + min(r0, H - 1)) * W + col, col, W, colvec && r0 < H, r0 < H);
+    }
 
 #pragma unroll 1
     for (int rr = 0; rr < R; ++rr) {
-        const int row = row0 + rr * kWarps;
-        if (row >= H) break;                 // warp-uniform; lanes past W stay active (predicated)
-        const float v = p.ys ? __ldg(p.ys + row) : mesh_coord(row, H);
-        const size_t rowbase = ((size_t)b * H + row) * W + col;   // C == 1 offset
+        if (band0 + rr * 8 >= H) break;      // warp-uniform
+        const int row = band0 + rr * 8 + ly;
+        const bool row_ok = row < H;
+        const int rowc = min(row, H - 1);
+        const size_t rowbase = ((size_t)b * H + rowc) * W + col;   // C == 1 offset
+        const bool vec = colvec && row_ok;
+        const int pc = classify ? s_patch[rr][warp] : -1;
 
-        // ---- software pipeline: this row's gt was requested one iteration ago; request the next ----
+        // ---- software pipeline: this band's gt was requested one iteration ago; request the next ----
         float tgt[4];
         if (EPI == kEpiLoss) {
             const Gt4 g = gnext;
-            if (rr + 1 < R && row + kWarps < H)
-                gnext = load_gt(p.gt, rowbase + (size_t)kWarps * W, col, W, full);
+            if (rr + 1 < R) {
+                const int rn = row + 8;
+                gnext = load_gt(p.gt, ((size_t)b * H + min(rn, H - 1)) * W + col, col, W, colvec && rn < H, rn < H);
+            }
             const float gf[4] = {(float)(int)g.lo.x, (float)(int)g.lo.y, (float)(int)g.hi.x, (float)(int)g.hi.y};
 #pragma unroll
             for (int j = 0; j < 4; ++j)      // class ids: the low 32 bits carry the value
-                tgt[j] = p.nc_pow2 ? __fmul_rn(gf[j], p.inv_nc) : __fdiv_rn(gf[j], (float)p.nc);
+                tgt[j] = p.nc_pow2 ? __fmul_rn(gf[j], p.inv_nc) : __fdiv_rn(gf[j], ncf);
         }
 
+        if (pc >= 0) {
+            // ================= edge-free patch: every pixel samples class `pc` =================
+            const float cval = taps.class_value(pc);
+            if (EPI == kEpiStore) {
+                const size_t off = (((size_t)b * C) * H + rowc) * W + col;
+                if (vec) __stcs((float4*)(p.out_f + off), make_float4(cval, cval, cval, cval));
+                else
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (row_ok && col + j < W) p.out_f[off + j] = cval;
+            }
+            if (EPI == kEpiLoss) {
+                if (p.out_f) {
+                    if (vec) __stcs((float4*)(p.out_f + rowbase), make_float4(cval, cval, cval, cval));
+                    else
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (row_ok && col + j < W) p.out_f[rowbase + j] = cval;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d = cval - tgt[j];
+                    float l = (p.kind == SFH_LOSS_MSE || fabsf(d) < 1.0f) ? d * d : 2.0f * fabsf(d) - 1.0f;
+                    if (!(row_ok && col + j < W)) l = 0.f;
+                    loss_sum += l;
+                }
+            }
+            if (EPI == kEpiPredict) {
+                const int ci = __float2int_rz(__fmul_rn(cval, ncf));
+                if (vec) __stcs((int4*)(p.out_i + rowbase), make_int4(ci, ci, ci, ci));
+                else
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (row_ok && col + j < W) p.out_i[rowbase + j] = ci;
+                if (p.score && p.ratio == 1 && row_ok) {
+                    const size_t cs = (size_t)p.lh * p.lw;
+                    const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)row * p.lw + col;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < W) score_sum += ce_pixel(lg + j, cs, p.nc, ci);
+                } else if (p.score && p.ratio == 2 && row_ok && !(row & 1)) {
+                    const size_t cs = (size_t)p.lh * p.lw;
+                    const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)(row >> 1) * p.lw + (col >> 1);
+                    if (col < W) score_sum += ce_pixel(lg, cs, p.nc, ci);
+                    if (col + 2 < W) score_sum += ce_pixel(lg + 1, cs, p.nc, ci);
+                }
+            }
+            continue;                        // kEpiBwd: zero gradient, grad_out is not even read
+        }
+
+        // ======================= per-pixel path (patch touches a class edge) ====================
+        const float v = p.ys ? __ldg(p.ys + rowc) : mesh_coord(rowc, H);
         Pix px[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) px[j] = pixel_geom<MODE>(Hm, pu0[j], pu3[j], pu6[j], v, Wc_f, Hc_f);
@@ -243,15 +367,15 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         if (EPI == kEpiStore || EPI == kEpiBwd) {
             float gix[4] = {0.f, 0.f, 0.f, 0.f}, giy[4] = {0.f, 0.f, 0.f, 0.f};
             for (int c = 0; c < C; ++c) {
-                const size_t off = (((size_t)b * C + c) * H + row) * W + col;
+                const size_t off = (((size_t)b * C + c) * H + rowc) * W + col;
                 float o[4], go[4];
                 if (EPI == kEpiBwd) {
-                    if (full) {
+                    if (vec) {
                         const float4 t4 = __ldcs((const float4*)(p.grad_out + off));
                         go[0] = t4.x; go[1] = t4.y; go[2] = t4.z; go[3] = t4.w;
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) go[j] = (col + j < W) ? __ldcs(p.grad_out + off + j) : 0.f;
+                        for (int j = 0; j < 4; ++j) go[j] = (row_ok && col + j < W) ? __ldcs(p.grad_out + off + j) : 0.f;
                     }
                 }
 #pragma unroll
@@ -268,18 +392,16 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                     }
                 }
                 if (EPI == kEpiStore) {
-                    if (full) {
-                        __stcs((float4*)(p.out_f + off), make_float4(o[0], o[1], o[2], o[3]));
-                    } else {
+                    if (vec) __stcs((float4*)(p.out_f + off), make_float4(o[0], o[1], o[2], o[3]));
+                    else
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) if (col + j < W) p.out_f[off + j] = o[j];
-                    }
+                        for (int j = 0; j < 4; ++j) if (row_ok && col + j < W) p.out_f[off + j] = o[j];
                 }
             }
             if (EPI == kEpiBwd) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (col + j < W) acc.add(px[j], gix[j], giy[j], halfWc, halfHc, u[j]);
+                for (int j = 0; j < 4; ++j)      // go is 0 outside the image, so no extra predicate
+                    acc.add(px[j], gix[j], giy[j], halfWc, halfHc, u[j]);
                 acc.end_row(v);
             }
         }
@@ -295,12 +417,10 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                 any_edge |= !t[j].uni;
             }
             if (p.out_f) {
-                if (full) {
-                    __stcs((float4*)(p.out_f + rowbase), make_float4(o[0], o[1], o[2], o[3]));
-                } else {
+                if (vec) __stcs((float4*)(p.out_f + rowbase), make_float4(o[0], o[1], o[2], o[3]));
+                else
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) if (col + j < W) p.out_f[rowbase + j] = o[j];
-                }
+                    for (int j = 0; j < 4; ++j) if (row_ok && col + j < W) p.out_f[rowbase + j] = o[j];
             }
             float g[4];
 #pragma unroll
@@ -312,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                 } else {
                     l = 2.0f * fabsf(d) - 1.0f; g[j] = d > 0.f ? 1.0f : -1.0f;   // doubled, halved below
                 }
-                if (col + j >= W) { l = 0.f; g[j] = 0.f; }
+                if (!(row_ok && col + j < W)) { l = 0.f; g[j] = 0.f; }
                 loss_sum += l;
                 g[j] *= gscale;
             }
@@ -336,21 +456,19 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                 float o;
                 if (MODE == SFH_MODE_NEAREST) o = taps.fetch1(0, px[j].x0, px[j].y0);
                 else o = bilerp(px[j], taps.fetch4(0, px[j].x0, px[j].y0));
-                cls[j] = __float2int_rz(__fmul_rn(o, (float)p.nc));   // (warp*nc).int()
+                cls[j] = __float2int_rz(__fmul_rn(o, ncf));   // (warp*nc).int()
             }
-            if (full) {
-                __stcs((int4*)(p.out_i + rowbase), make_int4(cls[0], cls[1], cls[2], cls[3]));
-            } else {
+            if (vec) __stcs((int4*)(p.out_i + rowbase), make_int4(cls[0], cls[1], cls[2], cls[3]));
+            else
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (col + j < W) p.out_i[rowbase + j] = cls[j];
-            }
-            if (p.score && p.ratio == 1) {
+                for (int j = 0; j < 4; ++j) if (row_ok && col + j < W) p.out_i[rowbase + j] = cls[j];
+            if (p.score && p.ratio == 1 && row_ok) {
                 const size_t cs = (size_t)p.lh * p.lw;
                 const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)row * p.lw + col;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (col + j < W) score_sum += ce_pixel(lg + j, cs, p.nc, cls[j]);
-            } else if (p.score && p.ratio == 2 && !(row & 1)) {
+            } else if (p.score && p.ratio == 2 && row_ok && !(row & 1)) {
                 // F.interpolate(nearest) to (H/2, W/2) picks source pixel (2i, 2j)
                 const size_t cs = (size_t)p.lh * p.lw;
                 const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)(row >> 1) * p.lw + (col >> 1);
@@ -508,6 +626,40 @@ __global__ void k_pack(const float* tmpl, int Hc, int Wc, T* q, int pitch, int n
     q[(size_t)j * pitch + i] = (T)v;
 }
 
+// Summed-area table of edge entries (see sfh_template.sat): row prefix sums, then column sums.
+template <int BITS, typename T>
+__global__ void __launch_bounds__(32) k_sat_rows(const T* q, int pitch, int Wc, unsigned* S, int sp) {
+    constexpr unsigned kMask = (1u << BITS) - 1u, kRep = (BITS == 2) ? 0x55u : 0x1111u;
+    const int j = blockIdx.x, lane = threadIdx.x;           // packed row 0..Hc+1
+    unsigned run = 0;
+    for (int i0 = 0; i0 <= Wc + 1; i0 += 32) {
+        const int i = i0 + lane;
+        unsigned e = 0;
+        if (i <= Wc + 1) {
+            const unsigned v = q[(size_t)j * pitch + i];
+            e = (v != (v & kMask) * kRep) ? 1u : 0u;
+        }
+        unsigned inc = e;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (i <= Wc + 1) S[(size_t)(j + 1) * sp + (i + 1)] = run + inc;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+__global__ void k_sat_cols(unsigned* S, int sp, int rows, int cols) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;   // table column 1..cols
+    if (i > cols) return;
+    unsigned acc = 0;
+    for (int j = 1; j <= rows; ++j) {
+        acc += S[(size_t)j * sp + i];
+        S[(size_t)j * sp + i] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -520,6 +672,7 @@ static int check_template(const sfh_template* t) {
         if (t->channels != 1 || t->pitch < t->width + 2) return SFH_E_BADARG;
         if (t->n_palette < 1 || t->n_palette > (t->fmt == SFH_TMPL_Q2 ? 4 : 16)) return SFH_E_BADARG;
         if (t->palette[0] != 0.0f) return SFH_E_BADARG;
+        if (t->sat && t->sat_pitch < t->width + 3) return SFH_E_BADARG;
         return 0;
     }
     return SFH_E_BADFMT;
@@ -598,7 +751,9 @@ int64_t sfh_workspace_bytes(int B, int H, int W) {
 }
 
 int sfh_template_pack(const float* tmpl, int Hc, int Wc, const float* palette_host, int n_palette,
-                      void* packed, int pitch, int fmt, int32_t* err_flag, void* stream) {
+                      void* packed, int pitch, int fmt, int32_t* err_flag,
+                      uint32_t* sat, int sat_pitch, void* stream) {
+    if (sat && sat_pitch < Wc + 3) return SFH_E_BADARG;
     if (!tmpl || !packed || !palette_host || !err_flag || Hc <= 0 || Wc <= 0 || pitch < Wc + 2) return SFH_E_BADARG;
     const int cap = fmt == SFH_TMPL_Q2 ? 4 : fmt == SFH_TMPL_Q4 ? 16 : 0;
     if (!cap) return SFH_E_BADFMT;
@@ -610,6 +765,11 @@ int sfh_template_pack(const float* tmpl, int Hc, int Wc, const float* palette_ho
     cudaStream_t st = (cudaStream_t)stream;
     if (fmt == SFH_TMPL_Q2) k_pack<2, uint8_t><<<grid, block, 0, st>>>(tmpl, Hc, Wc, (uint8_t*)packed, pitch, n_palette, pal, err_flag);
     else                    k_pack<4, uint16_t><<<grid, block, 0, st>>>(tmpl, Hc, Wc, (uint16_t*)packed, pitch, n_palette, pal, err_flag);
+    if (sat) {
+        if (fmt == SFH_TMPL_Q2) k_sat_rows<2, uint8_t><<<Hc + 2, 32, 0, st>>>((const uint8_t*)packed, pitch, Wc, sat, sat_pitch);
+        else                    k_sat_rows<4, uint16_t><<<Hc + 2, 32, 0, st>>>((const uint16_t*)packed, pitch, Wc, sat, sat_pitch);
+        k_sat_cols<<<(Wc + 2 + 127) / 128, 128, 0, st>>>(sat, sat_pitch, Hc + 2, Wc + 2);
+    }
     return (int)cudaGetLastError();
 }
 

@@ -110,7 +110,7 @@ def _launch_train_tail(stage, theta9, gt_masks, kind, want_mask, gt_poi, nonzero
         a.rec_lambda, a.reproj_lambda = float(rec_lambda), float(reproj_lambda)
         a.loss_out, a.dtheta_total = loss.data_ptr(), dtot.data_ptr()
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-    d = stage.template.desc()
+    d = stage.template.desc(stage.warper.edge_shortcut)
     with torch.cuda.device(dev):
         rc = _lib.lib().sfh_warp_loss_fwd_bwd(d, a, _stream())
     _lib.check(rc, "sfh_warp_loss_fwd_bwd")
@@ -171,19 +171,20 @@ class STNWarpStage(torch.nn.Module):
     Arguments mirror the corresponding ``Reconstructor.__init__`` ones
     (models/reconstructor.py:36-49): ``court_img`` [B,1,Hc,Wc] fp32 CUDA, ``court_poi`` [B,N,2]
     fp32 CUDA in [-1,1] (or None), ``warp_size`` (W,H), ``mask_classes``, ``warp_with_nearest``.
-    ``grid_source`` selects whose meshgrid rounding is replayed (see ``meshgrid_factors``).
+    ``grid_source`` selects whose meshgrid rounding is replayed (see ``meshgrid_factors``);
+    ``exact=True`` disables the edge-free-patch shortcut of the bilinear path (see ``HomographyWarper``).
     """
 
     def __init__(self, court_img: torch.Tensor, court_poi: Optional[torch.Tensor] = None,
                  warp_size=(640, 360), mask_classes: int = 4, warp_with_nearest: bool = False,
-                 grid_source: str = "device"):
+                 grid_source: str = "device", exact: bool = False):
         super().__init__()
         self.width, self.height = int(warp_size[0]), int(warp_size[1])
         self.mask_classes = int(mask_classes)
         self.mode = "nearest" if warp_with_nearest else "bilinear"
         # plain attributes, like the reference: nothing enters state_dict()
         self.court_img = court_img
-        self.warper = HomographyWarper(self.height, self.width, mode=self.mode, grid_source=grid_source)
+        self.warper = HomographyWarper(self.height, self.width, mode=self.mode, grid_source=grid_source, exact=exact)
         self.template: CourtTemplate = self.warper.set_template(court_img)
         self.device = court_img.device
         if court_poi is not None:
@@ -264,7 +265,7 @@ class STNWarpStage(torch.nn.Module):
         if want_poi:
             a.court_poi, a.court_poi_bstride, a.poi_out = self.court_poi.data_ptr(), self.poi_bstride, poi.data_ptr()
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-        d = self.template.desc()
+        d = self.template.desc(self.warper.edge_shortcut)
         with torch.cuda.device(self.device):
             rc = _lib.lib().sfh_predict_tail(d, a, _stream())
         _lib.check(rc, "sfh_predict_tail")

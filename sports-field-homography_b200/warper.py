@@ -79,16 +79,16 @@ class _WarpFn(torch.autograd.Function):
     """out = warp(template, theta); backward -> dtheta only (the template carries no gradient)."""
 
     @staticmethod
-    def forward(ctx, theta9, tmpl: CourtTemplate, xs, ys, H, W, mode):
+    def forward(ctx, theta9, tmpl: CourtTemplate, xs, ys, H, W, mode, shortcut):
         B = theta9.shape[0]
         out = torch.empty((B, tmpl.C, H, W), dtype=torch.float32, device=theta9.device)
-        d = tmpl.desc()
+        d = tmpl.desc(shortcut)
         with torch.cuda.device(theta9.device):
             rc = _lib.lib().sfh_warp_fwd(theta9.data_ptr(), d, _ptr(xs), _ptr(ys), B, H, W,
                                          _lib.MODE[mode], out.data_ptr(), _stream())
         _lib.check(rc, "sfh_warp_fwd")
         ctx.save_for_backward(theta9)
-        ctx.tmpl, ctx.xs, ctx.ys, ctx.mode, ctx.hw = tmpl, xs, ys, mode, (H, W)
+        ctx.tmpl, ctx.xs, ctx.ys, ctx.mode, ctx.hw, ctx.shortcut = tmpl, xs, ys, mode, (H, W), shortcut
         return out
 
     @staticmethod
@@ -97,19 +97,19 @@ class _WarpFn(torch.autograd.Function):
         B = theta9.shape[0]
         H, W = ctx.hw
         if ctx.mode == "nearest":           # piecewise-constant in theta: autograd gives zeros too
-            return torch.zeros_like(theta9), None, None, None, None, None, None
+            return torch.zeros_like(theta9), None, None, None, None, None, None, None
         grad_out = grad_out.contiguous()
         if grad_out.dtype != torch.float32:
             raise TypeError("grad_out must be float32")
         dth = torch.empty_like(theta9)
         ws = _WS.get(theta9.device, B, H, W)
-        d = ctx.tmpl.desc()
+        d = ctx.tmpl.desc(ctx.shortcut)
         with torch.cuda.device(theta9.device):
             rc = _lib.lib().sfh_warp_bwd(theta9.data_ptr(), d, _ptr(ctx.xs), _ptr(ctx.ys),
                                          grad_out.data_ptr(), B, H, W, dth.data_ptr(),
                                          ws.data_ptr(), ws.numel(), _stream())
         _lib.check(rc, "sfh_warp_bwd")
-        return dth, None, None, None, None, None, None
+        return dth, None, None, None, None, None, None, None
 
 
 class HomographyWarper(torch.nn.Module):
@@ -123,8 +123,13 @@ class HomographyWarper(torch.nn.Module):
 
     def __init__(self, height: int, width: int, mode: str = "bilinear", padding_mode: str = "zeros",
                  normalized_coordinates: bool = True, align_corners: bool = False,
-                 grid_source: str = "device") -> None:
+                 grid_source: str = "device", exact: bool = False) -> None:
         super().__init__()
+        # exact=True: every pixel is evaluated in ATen's fp32 operation order (bit-identical floats).
+        # exact=False (default): 16x8 output patches whose sampling footprint contains no class edge
+        # of a staged palette template are written as the class constant — bit-exact for 'nearest',
+        # within 2 ulp (2e-7) of ATen's interpolated constant for 'bilinear', gradients unchanged.
+        self.exact = bool(exact)
         if grid_source not in ("device", "cpu"):
             raise ValueError("grid_source must be 'device' or 'cpu'")
         self.grid_source = grid_source
@@ -138,6 +143,10 @@ class HomographyWarper(torch.nn.Module):
         self.normalized_coordinates, self.align_corners = normalized_coordinates, align_corners
         self._grid = {}          # device -> (xs, ys); plain attributes, nothing enters state_dict
         self._staged = None      # (key, CourtTemplate)
+
+    @property
+    def edge_shortcut(self) -> bool:
+        return self.mode == "nearest" or not self.exact
 
     def grid_factors(self, device):
         g = self._grid.get(device)
@@ -176,7 +185,7 @@ class HomographyWarper(torch.nn.Module):
         theta9 = check_theta(src_homo_dst, patch_src.device)
         tmpl = self._template_for(patch_src, theta9.shape[0])
         xs, ys = self.grid_factors(patch_src.device)
-        return _WarpFn.apply(theta9, tmpl, xs, ys, self.height, self.width, self.mode)
+        return _WarpFn.apply(theta9, tmpl, xs, ys, self.height, self.width, self.mode, self.edge_shortcut)
 
 
 class _TransformPointsFn(torch.autograd.Function):

@@ -36,11 +36,14 @@ def cu(a, dtype=None):
     return t.to(DEV)
 
 
-def mk_stage(*a, grid_source="cpu", **k):
+def mk_stage(*a, grid_source="cpu", exact=True, **k):
     """Tests compare against CPU-built oracles / golden vectors, so by default the stage replays
     the CPU meshgrid rounding; `grid_source="device"` is checked against ATen run on the GPU
-    (see sfh_b200.meshgrid_factors: this is the only fp32 difference between the two)."""
-    return sfh_b200.STNWarpStage(*a, grid_source=grid_source, **k)
+    (see sfh_b200.meshgrid_factors: this is the only fp32 difference between the two).
+    `exact=True` evaluates every pixel in ATen's operation order; the default production mode
+    (edge-free patches written as constants) is checked against it in
+    test_edge_free_patch_shortcut_*."""
+    return sfh_b200.STNWarpStage(*a, grid_source=grid_source, exact=exact, **k)
 
 
 def relnorm(a, b):
@@ -351,6 +354,80 @@ def test_transform_points_matches_kornia_restatement():
     kr.transform_points(t64, p64).backward(go.double())
     assert relnorm(trg.grad.cpu().numpy(), t64.grad.numpy()).max() <= TOL_GRAD
     np.testing.assert_allclose(pg.grad.cpu().numpy(), p64.grad.numpy(), rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------- production mode: edge-free patch shortcut
+SHORTCUT_CASES = [(640, 360, 16, "a", "ncaa_nc4"), (640, 360, 8, "b", "ncaa_nc4"), (1280, 720, 6, "a", "ncaa_nc4"),
+                  (1280, 720, 6, "b", "pitch_v3_nc4"), (200, 77, 5, "a", "ncaa_nc4"), (130, 50, 3, "b", "ncaa_nc4")]
+
+
+@pytest.mark.parametrize("W,H,B,fam,name", SHORTCUT_CASES)
+def test_edge_free_patch_shortcut_matches_exact_mode(W, H, B, fam, name):
+    """exact=False writes 16x8 patches that sample a single class as constants.  Versus the exact
+    mode: nearest / int32 masks identical, bilinear floats within 2 ulp of the class value, losses
+    within 1e-6 relative, dtheta IDENTICAL (such patches have exactly zero gradient in ATen too)."""
+    size = (1280, 720) if W > 640 else (640, 360)
+    tmpl, poi = sfh_b200.load_bundled(name, size, 4, 1)
+    th = _thetas(fam, B, 31).to(DEV)
+    if fam == "b":
+        th[0] = th[0] * 0 + torch.tensor([[1.0, 0.2, 0.1], [0.0, 1.0, 0.0], [0.9, 0.8, 0.3]], device=DEV)  # horizon inside the frame
+    kw = dict(grid_source="cpu")
+    ex = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, exact=True, **kw)
+    fa = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, exact=False, **kw)
+    we, wf = ex.warp(th), fa.warp(th)
+    d = (we - wf).abs()
+    assert float(d.max()) <= 2.5e-7, float(d.max())
+    assert float((d > 0).float().mean()) < 0.5
+    ref = co.warp_fwd(th.cpu().numpy(), tmpl.numpy(), H, W)[:, 0]
+    assert np.abs(wf.cpu().numpy() - ref).max() <= TOL_MASK
+    # training tail
+    gt = (co.warp_fwd(synth.perturb(th.cpu()).numpy(), tmpl.numpy(), H, W, "nearest")[:, 0] * 4).astype(np.int64)
+    w = torch.ones(B, dtype=torch.float64, device=DEV)
+    for kind in ("MSE", "SmoothL1"):
+        re_ = ex.train_step(th, cu(gt), w, kind)
+        rf = fa.train_step(th, cu(gt), w, kind)
+        np.testing.assert_allclose(rf["rec_per_sample"].cpu().numpy(), re_["rec_per_sample"].cpu().numpy(), rtol=1e-6)
+        assert torch.equal(rf["dtheta"], re_["dtheta"])
+        assert float((rf["warp_mask"] - re_["warp_mask"]).abs().max()) <= 2.5e-7
+    # generic backward: patches without an edge are skipped entirely
+    go = torch.randn(B, H, W, generator=torch.Generator().manual_seed(3)).to(DEV)
+    t1, t2 = th.clone().requires_grad_(True), th.clone().requires_grad_(True)
+    ex.warp(t1).backward(go)
+    fa.warp(t2).backward(go)
+    assert torch.equal(t1.grad, t2.grad)
+    # nearest (always uses the shortcut): bit-exact against the oracle, incl. the int32 predict mask
+    stn = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, warp_with_nearest=True, **kw)
+    refn = co.warp_fwd(th.cpu().numpy(), tmpl.numpy(), H, W, "nearest")[:, 0]
+    assert np.array_equal(stn.warp(th).cpu().numpy(), refn)
+    assert np.array_equal(stn.predict_tail(th, None, False, False)["warp_mask"].cpu().numpy(), (refn * 4).astype(np.int32))
+
+
+def test_edge_free_patch_shortcut_on_synthetic_templates():
+    """Stress the patch classifier: checkerboards (every patch has an edge), a constant image
+    (none has), thin lines, Q4 palettes, magnifying / minifying / mirrored homographies."""
+    rng = np.random.default_rng(5)
+    W, H = 256, 144
+    imgs = {
+        "const": np.full((90, 160), 0.5, np.float32),
+        "checker8": ((np.add.outer(np.arange(90) // 8, np.arange(160) // 8) % 2) * 0.75).astype(np.float32),
+        "line": np.where(np.abs(np.arange(160)[None, :] - 80) < 2, 0.25, 0.0).astype(np.float32) * np.ones((90, 1), np.float32),
+        "q4blocks": (rng.integers(0, 8, size=(9, 16)).repeat(10, 0).repeat(10, 1) / 8.0).astype(np.float32),
+    }
+    ths = torch.cat([synth.theta_family_a(4, 1, amp=0.4), synth.theta_family_b(3, 2),
+                     torch.tensor([[[[-1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0]]], [[[0.2, 0, 0], [0, 0.2, 0], [0, 0, 1.0]]],
+                                   [[[3.0, 0, 0], [0, 3.0, 0], [0, 0, 1.0]]], [[[0.0, 1.0, 0], [1.0, 0, 0], [0, 0, -1.0]]]])])
+    B = ths.shape[0]
+    for name, img in imgs.items():
+        t = torch.from_numpy(img)[None, None]
+        nc = 8 if name == "q4blocks" else 4
+        for nearest in (False, True):
+            st = sfh_b200.STNWarpStage(t.to(DEV), None, (W, H), nc, warp_with_nearest=nearest, grid_source="cpu")
+            out = st.warp(ths.to(DEV)).cpu().numpy()
+            ref = co.warp_fwd(ths.numpy(), img[None, None], H, W, "nearest" if nearest else "bilinear")[:, 0]
+            if nearest:
+                assert np.array_equal(out, ref), (name, (out != ref).mean())
+            else:
+                assert np.abs(out - ref).max() <= 2.5e-7, (name, np.abs(out - ref).max())
 
 
 # ----------------------------------------------------------------- size-independent properties
