@@ -12,6 +12,7 @@
 // owns rows {w, w+8} of a 128x16 tile.  The sampling grid lives in registers only.  Per-sample
 // sums (loss, 9 dtheta terms, score) go lane -> warp shuffle -> smem -> one partial per CTA; the
 // last CTA of a sample (ticket counter, no data atomics) adds the partials in fixed order in fp64.
+#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 #include "sfh_device.cuh"
@@ -20,14 +21,16 @@
 namespace sfh {
 
 struct FusedParams {
+    alignas(64) CUtensorMap gt_map;   // TMA descriptor of gt [B,H,W] int64, box 128 x 8R x 1
     const float* theta;
     const float* xs;
     const float* ys;
     sfh_template t;
     int B, H, W;
-    int rows_per_warp;   // R: a CTA covers 128 x 8R output pixels, warp w owns rows w, w+8, ...
+    int rows_per_warp;   // R: a CTA covers 128 x 8R output pixels = 8R patches of 16 x 8
     int ntiles;          // CTAs per sample
     int vec4;            // W % 4 == 0 and all row bases 16-byte aligned
+    int use_tma;         // kEpiLoss: the CTA's gt tile is staged in shared memory by one TMA load
     // kEpiStore / kEpiBwd
     float* out_f;        // [B,C,H,W]
     const float* grad_out;
@@ -146,9 +149,10 @@ __device__ __forceinline__ float ce_pixel(const float* lg, size_t cs, int nc, in
 
 struct Gt4 { longlong2 lo, hi; };
 
+template <bool FT>
 __device__ __forceinline__ Gt4 load_gt(const long long* gt, size_t rowbase, int col, int W, bool vec, bool row_ok) {
     Gt4 g;
-    if (vec) {
+    if (FT || vec) {
         g.lo = __ldcs((const longlong2*)(gt + rowbase));
         g.hi = __ldcs((const longlong2*)(gt + rowbase) + 1);
     } else {
@@ -160,6 +164,47 @@ __device__ __forceinline__ Gt4 load_gt(const long long* gt, size_t rowbase, int 
     return g;
 }
 
+// ---- TMA / mbarrier (sm_90+ PTX; SASS: UTMALDG / SYNCS) -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// Reduce 16 per-lane values across the warp with 16 shuffles: after the butterfly, lane L holds
+// the warp total of value  idx(L) = bit4(L)*8 + bit3(L)*4 + bit2(L)*2 + bit1(L).
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = up ? v[i + half] : v[i];
+            const float send = up ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 #ifndef SFH_MINCTAS_HEAVY
 #define SFH_MINCTAS_HEAVY 3   // loss / backward epilogues: <= 80 registers
 #endif
@@ -169,32 +214,40 @@ __device__ __forceinline__ Gt4 load_gt(const long long* gt, size_t rowbase, int 
 constexpr int min_ctas(int epi) { return (epi == kEpiStore || epi == kEpiPredict) ? SFH_MINCTAS_LIGHT : SFH_MINCTAS_HEAVY; }
 
 constexpr int kMaxR = 16;        // bands (8 rows each) per CTA
-constexpr int kPatchW = 16;      // a warp owns a 16 x 8 pixel patch per band: lane = (ly 0..7, lx 0..3), 4 px per lane
+constexpr int kPatchW = 16;      // a warp works on 16 x 8 pixel patches: lane = (ly 0..7, lx 0..3), 4 px per lane
 constexpr float kBoxMargin = 1.0f / 64.0f;   // slack (in texels) on the patch bounding box, >> fp32 rounding of ix
 
 // ------------------------------------------------------------------------------------------
 // The fused kernel.
 //
-// CTA tile: 128 x 8R output pixels of one sample; 8 warps side by side, each owning a 16-px-wide
-// column strip and walking down R bands of 8 rows.  Per band a lane owns 4 consecutive pixels of
-// one row: 4 lanes cover 64 B (fp32/int32 out) or 128 B (int64 gt) of a row, the 8 warps of the
-// CTA together 512 B / 1 KiB contiguous.
+// CTA tile: 128 x 8R output pixels of one sample = 8R patches of 16 x 8.  A warp processes one
+// patch at a time; a lane owns 4 consecutive pixels of one patch row, so 4 lanes cover 64 B
+// (fp32/int32 out) or 128 B (int64 gt) of a row.
 //
-// Court templates are piecewise-constant class maps, so most 16x8 patches sample one class only.
-// Before the pixel loop the CTA classifies its patches: x(u,v) = X/Z and y(u,v) are monotone in u
-// and in v as long as Z keeps its sign, hence the patch's sampling coordinates are bounded by the
-// values at its 4 corners; a summed-area table of "footprint straddles a class edge" over the
-// packed template answers "any edge inside the bounding box?" with 4 loads.  Edge-free patches
-// store the class value directly (their theta-gradient is exactly zero, as in ATen where the four
-// taps cancel); only patches on class edges run the per-pixel homography + bilinear + chain rule.
+// Court templates are piecewise-constant class maps, so most patches sample one class only.  The
+// CTA first classifies its patches: x(u,v) = X/Z and y(u,v) are monotone in u and in v as long as
+// Z keeps its sign, hence a patch's sampling coordinates are bounded by their values at the 4
+// corners; a summed-area table of "footprint straddles a class edge" over the packed template
+// answers "any edge inside that bounding box?" with 4 loads.  Edge-free patches store the class
+// value directly (their theta-gradient is exactly zero — in ATen the four taps cancel); only
+// patches on class edges run the per-pixel homography + bilinear + chain rule.  Patches are then
+// dealt to the 8 warps round-robin from a list with the expensive (edge) ones first, a static,
+// deterministic schedule that keeps the warps of a CTA within one patch of each other.
+//
+// kEpiLoss: the CTA's int64 gt tile (128 x 8R x 8 B) is fetched by ONE TMA tensor load issued at
+// kernel entry, so it streams in behind the classification prologue and the pixel loop never
+// waits on a global load.
 // ------------------------------------------------------------------------------------------
-template <int FMT, int MODE, int EPI>
+template <int FMT, int MODE, int EPI, bool FT>
 __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_constant__ FusedParams p) {
+    extern __shared__ __align__(128) unsigned char s_dyn[];            // TMA destination (gt tile)
     __shared__ __align__(16) float s_tab[Taps<FMT>::kSmemFloats];
-    __shared__ float s_red[kWarps][kNPart];
+    __shared__ float s_red[kWarps][16];
     __shared__ double s_fin[kNPart][kFinGroup];
     __shared__ float s_gx[kMaxR + 1][kWarps + 1], s_gy[kMaxR + 1][kWarps + 1], s_gz[kMaxR + 1][kWarps + 1];
-    __shared__ int s_patch[kMaxR][kWarps];   // palette index of an edge-free patch, -1: per-pixel path
+    __shared__ unsigned short s_items[kMaxR * kWarps];   // patch id | (class+1) << 8, edge patches first
+    __shared__ int s_ecnt[kWarps];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_last;
 
     const int b = blockIdx.z, tx = blockIdx.x, ty = blockIdx.y;
@@ -203,9 +256,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane & 3, ly = lane >> 2;
     const int R = p.rows_per_warp;
-    const int band0 = ty * (8 * R);          // first row of the CTA tile
+    const int band0 = ty * (8 * R);                       // first row of the CTA tile
+    const int nitems = min(R, (H - band0 + 7) >> 3) * kWarps;   // patches with at least one row inside the image
     const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
+    const bool tma = (EPI == kEpiLoss) && p.use_tma;
 
+    if (tma && threadIdx.x == 0) mbar_init(&s_bar, 1);
     Taps<FMT> taps;
     taps.build_tables(p.t, s_tab);
     if ((EPI == kEpiLoss || EPI == kEpiPredict) && tile == 0 && p.poi.court_poi)
@@ -223,11 +279,16 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         const Flow f = flow_at(Hm, __fmul_rn(gu, Hm.h[0]), __fmul_rn(gu, Hm.h[3]), __fmul_rn(gu, Hm.h[6]), gv);
         s_gx[r][k] = __fmul_rn(__fmaf_rn(__fadd_rn(f.x, 1.0f), Wc_f, -1.0f), 0.5f);
         s_gy[r][k] = __fmul_rn(__fmaf_rn(__fadd_rn(f.y, 1.0f), Hc_f, -1.0f), 0.5f);
-        s_gz[r][k] = f.zok ? __fdividef(1.0f, f.s) : __int_as_float(0x7fc00000);   // sign/size of Z; NaN poisons the patch
+        s_gz[r][k] = f.zok ? __fdividef(1.0f, f.s) : __int_as_float(0x7fc00000);   // sign of Z; NaN poisons the patch
     }
-    __syncthreads();
+    __syncthreads();                         // s_bar initialised, tables and corner grid written
+    if (tma && threadIdx.x == 0) {
+        mbar_expect_tx(&s_bar, (uint32_t)(R * 8 * kTileW * sizeof(long long)));
+        tma_load_3d(s_dyn, &p.gt_map, tx * kTileW, band0, b, &s_bar);
+    }
     taps.init(p.t, b, s_tab);
-    if (classify && threadIdx.x < kWarps * R) {
+    int cls = -1;
+    if (classify && threadIdx.x < nitems) {
         const int r = threadIdx.x / kWarps, k = threadIdx.x % kWarps;
         const float x00 = s_gx[r][k], x01 = s_gx[r][k + 1], x10 = s_gx[r + 1][k], x11 = s_gx[r + 1][k + 1];
         const float y00 = s_gy[r][k], y01 = s_gy[r][k + 1], y10 = s_gy[r + 1][k], y11 = s_gy[r + 1][k + 1];
@@ -240,7 +301,6 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         const bool fin = (x00 == x00) & (x01 == x01) & (x10 == x10) & (x11 == x11) &
                          (y00 == y00) & (y01 == y01) & (y10 == y10) & (y11 == y11) &
                          (xmin > -1e9f) & (xmax < 1e9f) & (ymin > -1e9f) & (ymax < 1e9f);
-        int cls = -1;
         if ((zpos | zneg) & fin) {
             // packed-template entries any pixel of the patch can touch (bilinear: floor+1,
             // nearest: rint+1 <= floor+2), clamped onto the all-zero border like the sampler does
@@ -255,55 +315,56 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                                - __ldg(S + (j1 + 1) * sp + i0) + __ldg(S + j0 * sp + i0);
             if (cnt == 0u) cls = (int)taps.entry_class(i0, j0);
         }
-        s_patch[r][k] = cls;
+    }
+    // ---- static schedule: list the edge patches first, warps then take entries w, w+8, ... ----
+    const bool is_edge = (threadIdx.x < nitems) && (cls < 0);
+    const unsigned bal = __ballot_sync(0xffffffffu, is_edge);
+    if (lane == 0) s_ecnt[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x < nitems) {
+        int before = __popc(bal & ((1u << lane) - 1u)), total = 0;
+#pragma unroll
+        for (int w = 0; w < kMaxR * kWarps / 32; ++w) {
+            const int c = s_ecnt[w];
+            total += c;
+            if (w < warp) before += c;
+        }
+        const int pos = is_edge ? before : total + ((int)threadIdx.x - before);
+        s_items[pos] = (unsigned short)(threadIdx.x | ((cls + 1) << 8));
     }
     __syncthreads();
 
-    const int col = tx * kTileW + warp * kPatchW + lx * 4;
     const int C = (FMT == SFH_TMPL_F32) ? p.t.channels : 1;
     const float halfWc = 0.5f * Wc_f, halfHc = 0.5f * Hc_f;
-
-    // column invariants: u and the first bmm product u*h{0,3,6}
-    float u[4], pu0[4], pu3[4], pu6[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int cx = min(col + j, W - 1);
-        u[j] = p.xs ? __ldg(p.xs + cx) : mesh_coord(cx, W);
-        pu0[j] = __fmul_rn(u[j], Hm.h[0]);
-        pu3[j] = __fmul_rn(u[j], Hm.h[3]);
-        pu6[j] = __fmul_rn(u[j], Hm.h[6]);
-    }
-
     GradAcc acc;
     acc.zero();
     float loss_sum = 0.f, score_sum = 0.f;
-    const bool colvec = p.vec4 && (col + 3 < W);
     const float gscale = (p.kind == SFH_LOSS_MSE ? 2.0f : 1.0f) * p.invN;
     const float ncf = (float)p.nc;
+    const long long* s_gt = reinterpret_cast<const long long*>(s_dyn);
 
-    Gt4 gnext;
-    if (EPI == kEpiLoss) {
-        const int r0 = band0 + ly;
-        gnext = load_gt(p.gt, ((size_t)b * H + min(r0, H - 1)) * W + col, col, W, colvec && r0 < H, r0 < H);
-    }
+    if (tma) mbar_wait(&s_bar, 0);           // gt tile has landed (it streamed in behind the prologue)
 
 #pragma unroll 1
-    for (int rr = 0; rr < R; ++rr) {
-        if (band0 + rr * 8 >= H) break;      // warp-uniform
-        const int row = band0 + rr * 8 + ly;
-        const bool row_ok = row < H;
-        const int rowc = min(row, H - 1);
+    for (int it = warp; it < nitems; it += kWarps) {
+        const unsigned item = s_items[it];
+        const int pr = (item & 0xffu) >> 3, pk = item & 7u, pc = (int)(item >> 8) - 1;
+        const int row = band0 + pr * 8 + ly;
+        const int col = tx * kTileW + pk * kPatchW + lx * 4;
+        const bool row_ok = FT || row < H;
+        const int rowc = FT ? row : min(row, H - 1);
+        const bool vec = FT || (p.vec4 && row_ok && col + 3 < W);
         const size_t rowbase = ((size_t)b * H + rowc) * W + col;   // C == 1 offset
-        const bool vec = colvec && row_ok;
-        const int pc = classify ? s_patch[rr][warp] : -1;
+#define SFH_PIX_OK(j) (FT || (row_ok && col + (j) < W))
 
-        // ---- software pipeline: this band's gt was requested one iteration ago; request the next ----
         float tgt[4];
         if (EPI == kEpiLoss) {
-            const Gt4 g = gnext;
-            if (rr + 1 < R) {
-                const int rn = row + 8;
-                gnext = load_gt(p.gt, ((size_t)b * H + min(rn, H - 1)) * W + col, col, W, colvec && rn < H, rn < H);
+            Gt4 g;
+            if (tma) {                       // zero-filled outside the image by the TMA unit
+                const longlong2* sp2 = reinterpret_cast<const longlong2*>(s_gt + (pr * 8 + ly) * kTileW + pk * kPatchW + lx * 4);
+                g.lo = sp2[0]; g.hi = sp2[1];
+            } else {
+                g = load_gt<FT>(p.gt, rowbase, col, W, vec, row_ok);
             }
             const float gf[4] = {(float)(int)g.lo.x, (float)(int)g.lo.y, (float)(int)g.hi.x, (float)(int)g.hi.y};
 #pragma unroll
@@ -319,20 +380,20 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                 if (vec) __stcs((float4*)(p.out_f + off), make_float4(cval, cval, cval, cval));
                 else
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) if (row_ok && col + j < W) p.out_f[off + j] = cval;
+                    for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_f[off + j] = cval;
             }
             if (EPI == kEpiLoss) {
                 if (p.out_f) {
                     if (vec) __stcs((float4*)(p.out_f + rowbase), make_float4(cval, cval, cval, cval));
                     else
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) if (row_ok && col + j < W) p.out_f[rowbase + j] = cval;
+                        for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_f[rowbase + j] = cval;
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float d = cval - tgt[j];
                     float l = (p.kind == SFH_LOSS_MSE || fabsf(d) < 1.0f) ? d * d : 2.0f * fabsf(d) - 1.0f;
-                    if (!(row_ok && col + j < W)) l = 0.f;
+                    if (!SFH_PIX_OK(j)) l = 0.f;
                     loss_sum += l;
                 }
             }
@@ -341,18 +402,18 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                 if (vec) __stcs((int4*)(p.out_i + rowbase), make_int4(ci, ci, ci, ci));
                 else
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) if (row_ok && col + j < W) p.out_i[rowbase + j] = ci;
+                    for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_i[rowbase + j] = ci;
                 if (p.score && p.ratio == 1 && row_ok) {
                     const size_t cs = (size_t)p.lh * p.lw;
                     const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)row * p.lw + col;
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (col + j < W) score_sum += ce_pixel(lg + j, cs, p.nc, ci);
+                        if (FT || col + j < W) score_sum += ce_pixel(lg + j, cs, p.nc, ci);
                 } else if (p.score && p.ratio == 2 && row_ok && !(row & 1)) {
                     const size_t cs = (size_t)p.lh * p.lw;
                     const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)(row >> 1) * p.lw + (col >> 1);
-                    if (col < W) score_sum += ce_pixel(lg, cs, p.nc, ci);
-                    if (col + 2 < W) score_sum += ce_pixel(lg + 1, cs, p.nc, ci);
+                    if (FT || col < W) score_sum += ce_pixel(lg, cs, p.nc, ci);
+                    if (FT || col + 2 < W) score_sum += ce_pixel(lg + 1, cs, p.nc, ci);
                 }
             }
             continue;                        // kEpiBwd: zero gradient, grad_out is not even read
@@ -360,9 +421,22 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 
         // ======================= per-pixel path (patch touches a class edge) ====================
         const float v = p.ys ? __ldg(p.ys + rowc) : mesh_coord(rowc, H);
+        float u[4];
+        if (FT && p.xs) {
+            const float4 u4 = __ldg(reinterpret_cast<const float4*>(p.xs + col));
+            u[0] = u4.x; u[1] = u4.y; u[2] = u4.z; u[3] = u4.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int cx = min(col + j, W - 1);
+                u[j] = p.xs ? __ldg(p.xs + cx) : mesh_coord(cx, W);
+            }
+        }
         Pix px[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) px[j] = pixel_geom<MODE>(Hm, pu0[j], pu3[j], pu6[j], v, Wc_f, Hc_f);
+        for (int j = 0; j < 4; ++j)          // u*h{0,3,6}: the first product of the bmm chain
+            px[j] = pixel_geom<MODE>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]), __fmul_rn(u[j], Hm.h[6]),
+                                     v, Wc_f, Hc_f);
 
         if (EPI == kEpiStore || EPI == kEpiBwd) {
             float gix[4] = {0.f, 0.f, 0.f, 0.f}, giy[4] = {0.f, 0.f, 0.f, 0.f};
@@ -375,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                         go[0] = t4.x; go[1] = t4.y; go[2] = t4.z; go[3] = t4.w;
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) go[j] = (row_ok && col + j < W) ? __ldcs(p.grad_out + off + j) : 0.f;
+                        for (int j = 0; j < 4; ++j) go[j] = SFH_PIX_OK(j) ? __ldcs(p.grad_out + off + j) : 0.f;
                     }
                 }
 #pragma unroll
@@ -395,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                     if (vec) __stcs((float4*)(p.out_f + off), make_float4(o[0], o[1], o[2], o[3]));
                     else
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) if (row_ok && col + j < W) p.out_f[off + j] = o[j];
+                        for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_f[off + j] = o[j];
                 }
             }
             if (EPI == kEpiBwd) {
@@ -420,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                 if (vec) __stcs((float4*)(p.out_f + rowbase), make_float4(o[0], o[1], o[2], o[3]));
                 else
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) if (row_ok && col + j < W) p.out_f[rowbase + j] = o[j];
+                    for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_f[rowbase + j] = o[j];
             }
             float g[4];
 #pragma unroll
@@ -432,12 +506,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                 } else {
                     l = 2.0f * fabsf(d) - 1.0f; g[j] = d > 0.f ? 1.0f : -1.0f;   // doubled, halved below
                 }
-                if (!(row_ok && col + j < W)) { l = 0.f; g[j] = 0.f; }
+                if (!SFH_PIX_OK(j)) { l = 0.f; g[j] = 0.f; }
                 loss_sum += l;
                 g[j] *= gscale;
             }
             // the gradient lives on footprints that straddle a class edge; a uniform footprint
-            // cancels exactly (a*sy - a*sy), so whole warps skip the chain rule when none is on one
+            // cancels exactly (a*sy - a*sy), so a warp skips the chain rule when no lane is on one
             if (__any_sync(0xffffffffu, any_edge)) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -450,52 +524,50 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         }
 
         if (EPI == kEpiPredict) {
-            int cls[4];
+            int ci[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float o;
                 if (MODE == SFH_MODE_NEAREST) o = taps.fetch1(0, px[j].x0, px[j].y0);
                 else o = bilerp(px[j], taps.fetch4(0, px[j].x0, px[j].y0));
-                cls[j] = __float2int_rz(__fmul_rn(o, ncf));   // (warp*nc).int()
+                ci[j] = __float2int_rz(__fmul_rn(o, ncf));   // (warp*nc).int()
             }
-            if (vec) __stcs((int4*)(p.out_i + rowbase), make_int4(cls[0], cls[1], cls[2], cls[3]));
+            if (vec) __stcs((int4*)(p.out_i + rowbase), make_int4(ci[0], ci[1], ci[2], ci[3]));
             else
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (row_ok && col + j < W) p.out_i[rowbase + j] = cls[j];
+                for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_i[rowbase + j] = ci[j];
             if (p.score && p.ratio == 1 && row_ok) {
                 const size_t cs = (size_t)p.lh * p.lw;
                 const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)row * p.lw + col;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (col + j < W) score_sum += ce_pixel(lg + j, cs, p.nc, cls[j]);
+                    if (FT || col + j < W) score_sum += ce_pixel(lg + j, cs, p.nc, ci[j]);
             } else if (p.score && p.ratio == 2 && row_ok && !(row & 1)) {
                 // F.interpolate(nearest) to (H/2, W/2) picks source pixel (2i, 2j)
                 const size_t cs = (size_t)p.lh * p.lw;
                 const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)(row >> 1) * p.lw + (col >> 1);
-                if (col < W) score_sum += ce_pixel(lg, cs, p.nc, cls[0]);
-                if (col + 2 < W) score_sum += ce_pixel(lg + 1, cs, p.nc, cls[2]);
+                if (FT || col < W) score_sum += ce_pixel(lg, cs, p.nc, ci[0]);
+                if (FT || col + 2 < W) score_sum += ce_pixel(lg + 1, cs, p.nc, ci[2]);
             }
         }
     }
+#undef SFH_PIX_OK
 
     if (EPI == kEpiStore) return;
     if (EPI == kEpiPredict && !(p.score && p.ratio != 0)) return;
 
     // ---------------- per-sample reduction: lane -> warp -> CTA partial -> last CTA -----------
     if (EPI == kEpiLoss && p.kind != SFH_LOSS_MSE) loss_sum *= 0.5f;
-    float vals[kNPart];
-    vals[0] = loss_sum;
+    {
+        float vals[16];
+        vals[0] = loss_sum;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) vals[1 + k] = acc.a[k];
-    vals[10] = score_sum;
-    vals[11] = 0.f;
+        for (int k = 0; k < 9; ++k) vals[1 + k] = acc.a[k];
+        vals[10] = score_sum;
 #pragma unroll
-    for (int k = 0; k < kNPart - 1; ++k) {
-        if (EPI == kEpiBwd && (k == 0 || k == 10)) continue;
-        if (EPI == kEpiLoss && k == 10) continue;
-        if (EPI == kEpiPredict && k != 10) continue;
-        const float s = warp_sum(vals[k]);
-        if (lane == 0) s_red[warp][k] = s;
+        for (int k = 11; k < 16; ++k) vals[k] = 0.f;
+        const float tot = warp_reduce16(vals, lane);
+        if (!(lane & 1)) s_red[warp][((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = tot;
     }
     __syncthreads();
     if (threadIdx.x < kNPart) {
@@ -706,18 +778,67 @@ static int setup_ws(FusedParams& p, void* ws, int64_t ws_bytes) {
     return 0;
 }
 
+template <int FMT, int MODE, int EPI>
+static int launch_fmt(const FusedParams& p, dim3 grid, size_t dyn, bool ft, cudaStream_t st) {
+    auto kf = k_fused<FMT, MODE, EPI, true>;
+    auto kg = k_fused<FMT, MODE, EPI, false>;
+    if (dyn > 48 * 1024) {
+        static bool raised = false;            // per instantiation; idempotent, so a race is harmless
+        if (!raised) {
+            cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8 * kTileW * 8);
+            cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8 * kTileW * 8);
+            raised = true;
+        }
+    }
+    if (ft) kf<<<grid, kThreads, dyn, st>>>(p);
+    else    kg<<<grid, kThreads, dyn, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
 template <int MODE, int EPI>
 static int launch_fused(const FusedParams& p, cudaStream_t st) {
     if (p.B > 65535) return SFH_E_BADARG;
     const int tiles_x = (p.W + kTileW - 1) / kTileW;
-    dim3 grid(tiles_x, p.ntiles / tiles_x, p.B), block(kThreads);
+    dim3 grid(tiles_x, p.ntiles / tiles_x, p.B);
+    const bool ft = p.vec4 && (p.W % kTileW == 0) && (p.H % 8 == 0) &&
+                    (!p.xs || (((uintptr_t)p.xs & 15u) == 0));
+    const size_t dyn = (EPI == kEpiLoss && p.use_tma) ? (size_t)p.rows_per_warp * 8 * kTileW * sizeof(long long) : 0;
     switch (p.t.fmt) {
-        case SFH_TMPL_F32: k_fused<SFH_TMPL_F32, MODE, EPI><<<grid, block, 0, st>>>(p); break;
-        case SFH_TMPL_Q2:  k_fused<SFH_TMPL_Q2, MODE, EPI><<<grid, block, 0, st>>>(p); break;
-        case SFH_TMPL_Q4:  k_fused<SFH_TMPL_Q4, MODE, EPI><<<grid, block, 0, st>>>(p); break;
+        case SFH_TMPL_F32: return launch_fmt<SFH_TMPL_F32, MODE, EPI>(p, grid, dyn, ft, st);
+        case SFH_TMPL_Q2:  return launch_fmt<SFH_TMPL_Q2, MODE, EPI>(p, grid, dyn, ft, st);
+        case SFH_TMPL_Q4:  return launch_fmt<SFH_TMPL_Q4, MODE, EPI>(p, grid, dyn, ft, st);
         default: return SFH_E_BADFMT;
     }
-    return (int)cudaGetLastError();
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// gt [B,H,W] int64 -> 3-D tensor map, box 128 x 8R x 1 (one TMA load per CTA tile, OOB zero-filled)
+static bool make_gt_map(FusedParams& p) {
+    static const bool off = getenv("SFH_NO_TMA") != nullptr;
+    EncodeTiledFn enc = encode_tiled();
+    if (off || !enc || !aligned16(p.gt) || p.rows_per_warp > 8) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.W * 8, (cuuint64_t)p.W * p.H * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)kTileW, (cuuint32_t)(8 * p.rows_per_warp), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(&p.gt_map, CU_TENSOR_MAP_DATA_TYPE_INT64, 3, (void*)p.gt, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace sfh
@@ -831,6 +952,11 @@ int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* a
     p.weights = a->weights; p.w_f64 = a->weights_f64; p.w_outer = a->weights_outer;
     p.rec_lambda = a->rec_lambda; p.reproj_lambda = a->reproj_lambda;
     p.loss_out = a->loss_out; p.dtheta_total = a->dtheta_total;
+    if (p.rows_per_warp > 8) {               // keep the staged gt tile <= 64 KiB per CTA
+        p.rows_per_warp = 8;
+        p.ntiles = ((a->W + kTileW - 1) / kTileW) * ((a->H + 63) / 64);
+    }
+    p.use_tma = make_gt_map(p) ? 1 : 0;
     return launch_fused<SFH_MODE_BILINEAR, kEpiLoss>(p, (cudaStream_t)stream);
 }
 
