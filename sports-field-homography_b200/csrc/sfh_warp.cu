@@ -311,9 +311,10 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             const int j1 = min(max(__float2int_rd(ymax + kBoxMargin) + 2, 0), hmax);
             const unsigned* S = p.t.sat;
             const int sp = p.t.sat_pitch;
+            const unsigned ec = taps.entry_class(i0, j0);          // issued with the 4 table loads
             const unsigned cnt = __ldg(S + (j1 + 1) * sp + (i1 + 1)) - __ldg(S + j0 * sp + (i1 + 1))
                                - __ldg(S + (j1 + 1) * sp + i0) + __ldg(S + j0 * sp + i0);
-            if (cnt == 0u) cls = (int)taps.entry_class(i0, j0);
+            if (cnt == 0u) cls = (int)ec;
         }
     }
     // ---- static schedule: list the edge patches first, warps then take entries w, w+8, ... ----
@@ -483,12 +484,10 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         if (EPI == kEpiLoss) {
             float o[4];
             TapVals t[4];
-            bool any_edge = false;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 t[j] = taps.fetch4(0, px[j].x0, px[j].y0);
                 o[j] = bilerp(px[j], t[j]);
-                any_edge |= !t[j].uni;
             }
             if (p.out_f) {
                 if (vec) __stcs((float4*)(p.out_f + rowbase), make_float4(o[0], o[1], o[2], o[3]));
@@ -511,16 +510,19 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                 g[j] *= gscale;
             }
             // the gradient lives on footprints that straddle a class edge; a uniform footprint
-            // cancels exactly (a*sy - a*sy), so a warp skips the chain rule when no lane is on one
-            if (__any_sync(0xffffffffu, any_edge)) {
+            // cancels exactly (a*sy - a*sy), so the warp skips the chain rule for every pixel slot j
+            // on which no lane straddles one (a vertical court line touches 1-2 of the 4 slots)
+            bool any = false;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 4; ++j) {
+                if (__any_sync(0xffffffffu, !t[j].uni)) {
                     const float gix = ((t[j].b - t[j].a) * px[j].sy + (t[j].d - t[j].c) * px[j].ny) * g[j];
                     const float giy = ((t[j].c - t[j].a) * px[j].ex + (t[j].d - t[j].b) * px[j].wx) * g[j];
                     acc.add(px[j], gix, giy, halfWc, halfHc, u[j]);
+                    any = true;
                 }
-                acc.end_row(v);
             }
+            if (any) acc.end_row(v);
         }
 
         if (EPI == kEpiPredict) {
