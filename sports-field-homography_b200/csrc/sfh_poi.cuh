@@ -44,10 +44,8 @@ __device__ __forceinline__ void inv3x3(const double* a, double* m) {
     m[6] = c02 * r; m[7] = (a[1] * a[6] - a[0] * a[7]) * r; m[8] = (a[0] * a[4] - a[1] * a[3]) * r;
 }
 
-// Executed by the first warp of a CTA (the rest of the CTA leaves immediately).
-__device__ __forceinline__ void poi_block(const PoiParams& p, int b) {
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
+// Executed by ONE full warp (all 32 lanes call it together).
+__device__ __forceinline__ void poi_warp(const PoiParams& p, int b, int lane) {
     double a[9], m[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) a[k] = (double)__ldg(p.theta + 9 * b + k);
@@ -113,6 +111,11 @@ __device__ __forceinline__ void poi_block(const PoiParams& p, int b) {
                 dst[9 * b + 3 * i + j] = (float)(-acc);
             }
     }
+}
+
+// Executed by the first warp of a CTA (the other warps pass through).
+__device__ __forceinline__ void poi_block(const PoiParams& p, int b) {
+    if (threadIdx.x < 32) poi_warp(p, b, threadIdx.x);
 }
 
 }  // namespace sfh

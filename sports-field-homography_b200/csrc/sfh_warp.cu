@@ -649,6 +649,359 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     if (threadIdx.x == 0) p.counters[b] = 0;   // leave the workspace zeroed for the next call
 }
 
+// ------------------------------------------------------------------------------------------
+// Persistent, warp-specialised training kernel (kEpiLoss with a TMA-staged gt tile).
+//
+// One CTA per SM: 1 producer warp + 16 consumer warps, a 3-stage ring of 128 x 64 px tiles.
+//   producer   takes the next tile from a global ticket, issues ONE TMA tensor load for its int64
+//              gt tile (64 KiB), and while that is in flight loads theta, classifies the tile's 64
+//              patches against the edge summed-area table and writes the edge-first patch list
+//              into the stage; arrives on the stage's `full` mbarrier (TMA completes the tx count).
+//   consumers  wait on `full`, each takes patches cw, cw+16, ... of the list (per-pixel path for
+//              edge patches, constant path otherwise), flush their 10 sums for the tile with a
+//              16-value shuffle butterfly into a fixed slot, take a release ticket on the sample,
+//              and arrive on the stage's `empty` mbarrier.  No __syncthreads in the steady state.
+// The warp that takes a sample's last ticket sums that sample's slots in fixed order in fp64
+// (results do not depend on which SM processed which tile) and runs the optional batch combine.
+// ------------------------------------------------------------------------------------------
+constexpr int kPCons = 16;                       // consumer warps
+constexpr int kPThreads = 32 * (kPCons + 1);
+constexpr int kPStages = 3;
+constexpr int kPR = 8;                           // bands per tile
+constexpr int kPItems = kPR * kWarps;            // 64 patches per tile
+constexpr int kPTileBytes = kPR * 8 * kTileW * 8;
+
+struct PStage {
+    unsigned short items[kPItems];
+    float theta[9];
+    int b, tx, ty, nitems;                       // nitems < 0: no more tiles
+};
+
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+template <int FMT, bool FT>
+__global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_constant__ FusedParams p) {
+    extern __shared__ __align__(128) unsigned char s_dyn[];            // kPStages gt tiles (TMA destinations)
+    __shared__ __align__(16) float s_tab[Taps<FMT>::kSmemFloats];
+    __shared__ PStage s_stage[kPStages];
+    __shared__ float s_gx[kPR + 1][kWarps + 1], s_gy[kPR + 1][kWarps + 1], s_gz[kPR + 1][kWarps + 1];   // producer scratch
+    __shared__ __align__(8) uint64_t s_full[kPStages], s_empty[kPStages];
+
+    const int H = p.H, W = p.W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
+    const int tiles_x = (W + kTileW - 1) / kTileW;
+    const int tiles_y = (H + 8 * kPR - 1) / (8 * kPR);
+    const int tiles_per_sample = tiles_x * tiles_y;
+    const int total_tiles = tiles_per_sample * p.B;
+    int* tile_ctr = p.counters + p.B + 1;
+    int* done_ctr = p.counters + p.B + 2;
+
+    Taps<FMT> taps;
+    if (threadIdx.x < kThreads) taps.build_tables(p.t, s_tab);         // 256-entry LUT: first 256 threads
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kPStages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_full[s])), "r"(1) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_empty[s])), "r"(kPCons) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    taps.init(p.t, 0, s_tab);
+    const bool classify = (FMT != SFH_TMPL_F32) && (p.t.sat != nullptr);
+
+    if (warp == kPCons) {
+        // =================================== producer warp ===================================
+        for (int it = 0;; ++it) {
+            const int s = it % kPStages;
+            mbar_wait(&s_empty[s], ((it / kPStages) & 1) ^ 1);          // consumers released this stage
+            int t = 0;
+            if (lane == 0) t = atomicAdd(tile_ctr, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            PStage& st = s_stage[s];
+            if (t >= total_tiles) {
+                if (lane == 0) { st.nitems = -1; }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&s_full[s]);
+                    // the last CTA to run out of tiles re-zeroes the tile ticket for the next launch
+                    if (atomicAdd(done_ctr, 1) == (int)gridDim.x - 1) { *tile_ctr = 0; *done_ctr = 0; }
+                }
+                break;
+            }
+            const int b = t / tiles_per_sample, rem = t - b * tiles_per_sample;
+            const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+            const int band0 = ty * (8 * kPR);
+            const int nitems = min(kPR, (H - band0 + 7) >> 3) * kWarps;
+            if (lane == 0) {
+                mbar_expect_tx_only(&s_full[s], (uint32_t)kPTileBytes);
+                tma_load_3d(s_dyn + (size_t)s * kPTileBytes, &p.gt_map, tx * kTileW, band0, b, &s_full[s]);
+            }
+            Homog Hm;
+            Hm.load(p.theta + 9 * b);
+            if (rem == 0 && p.poi.court_poi) poi_warp(p.poi, b, lane);  // the sample's court points (fp64)
+            if (classify) {
+                for (int g = lane; g < (kWarps + 1) * (kPR + 1); g += 32) {
+                    const int r = g / (kWarps + 1), k = g - r * (kWarps + 1);
+                    const int grow = min(band0 + 8 * r, H - 1), gcol = min(tx * kTileW + kPatchW * k, W - 1);
+                    const float gu = p.xs ? __ldg(p.xs + gcol) : mesh_coord(gcol, W);
+                    const float gv = p.ys ? __ldg(p.ys + grow) : mesh_coord(grow, H);
+                    const Flow f = flow_at(Hm, __fmul_rn(gu, Hm.h[0]), __fmul_rn(gu, Hm.h[3]), __fmul_rn(gu, Hm.h[6]), gv);
+                    s_gx[r][k] = __fmul_rn(__fmaf_rn(__fadd_rn(f.x, 1.0f), Wc_f, -1.0f), 0.5f);
+                    s_gy[r][k] = __fmul_rn(__fmaf_rn(__fadd_rn(f.y, 1.0f), Hc_f, -1.0f), 0.5f);
+                    s_gz[r][k] = f.zok ? __fdividef(1.0f, f.s) : __int_as_float(0x7fc00000);
+                }
+                __syncwarp();
+            }
+            int cls[2] = {-1, -1};
+            if (classify) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int id = lane + 32 * h;
+                    if (id >= nitems) continue;
+                    const int r = id / kWarps, k = id % kWarps;
+                    const float x00 = s_gx[r][k], x01 = s_gx[r][k + 1], x10 = s_gx[r + 1][k], x11 = s_gx[r + 1][k + 1];
+                    const float y00 = s_gy[r][k], y01 = s_gy[r][k + 1], y10 = s_gy[r + 1][k], y11 = s_gy[r + 1][k + 1];
+                    const float z00 = s_gz[r][k], z01 = s_gz[r][k + 1], z10 = s_gz[r + 1][k], z11 = s_gz[r + 1][k + 1];
+                    const float xmin = fminf(fminf(x00, x01), fminf(x10, x11)), xmax = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11));
+                    const float ymin = fminf(fminf(y00, y01), fminf(y10, y11)), ymax = fmaxf(fmaxf(y00, y01), fmaxf(y10, y11));
+                    const bool zpos = (z00 > 0.f) & (z01 > 0.f) & (z10 > 0.f) & (z11 > 0.f);
+                    const bool zneg = (z00 < 0.f) & (z01 < 0.f) & (z10 < 0.f) & (z11 < 0.f);
+                    const bool fin = (x00 == x00) & (x01 == x01) & (x10 == x10) & (x11 == x11) &
+                                     (y00 == y00) & (y01 == y01) & (y10 == y10) & (y11 == y11) &
+                                     (xmin > -1e9f) & (xmax < 1e9f) & (ymin > -1e9f) & (ymax < 1e9f);
+                    if ((zpos | zneg) & fin) {
+                        const int wmax = p.t.width + 1, hmax = p.t.height + 1;
+                        const int i0 = min(max(__float2int_rd(xmin - kBoxMargin) + 1, 0), wmax);
+                        const int i1 = min(max(__float2int_rd(xmax + kBoxMargin) + 2, 0), wmax);
+                        const int j0 = min(max(__float2int_rd(ymin - kBoxMargin) + 1, 0), hmax);
+                        const int j1 = min(max(__float2int_rd(ymax + kBoxMargin) + 2, 0), hmax);
+                        const unsigned* S = p.t.sat;
+                        const int sp = p.t.sat_pitch;
+                        const unsigned ec = taps.entry_class(i0, j0);
+                        const unsigned cnt = __ldg(S + (j1 + 1) * sp + (i1 + 1)) - __ldg(S + j0 * sp + (i1 + 1))
+                                           - __ldg(S + (j1 + 1) * sp + i0) + __ldg(S + j0 * sp + i0);
+                        if (cnt == 0u) cls[h] = (int)ec;
+                    }
+                }
+            }
+            // edge-first patch list (single warp: two ballots give every rank)
+            const bool e0 = (lane < nitems) && cls[0] < 0, e1 = (lane + 32 < nitems) && cls[1] < 0;
+            const unsigned b0 = __ballot_sync(0xffffffffu, e0), b1 = __ballot_sync(0xffffffffu, e1);
+            const unsigned lt = (1u << lane) - 1u;
+            const int n0 = __popc(b0), total = n0 + __popc(b1);
+            if (lane < nitems) {
+                const int before = __popc(b0 & lt);
+                st.items[e0 ? before : total + (lane - before)] = (unsigned short)(lane | ((cls[0] + 1) << 8));
+            }
+            if (lane + 32 < nitems) {
+                const int before = n0 + __popc(b1 & lt);
+                st.items[e1 ? before : total + (lane + 32 - before)] = (unsigned short)((lane + 32) | ((cls[1] + 1) << 8));
+            }
+            if (lane < 9) st.theta[lane] = Hm.h[0] * 0.f + __ldg(p.theta + 9 * b + lane);
+            if (lane == 0) { st.b = b; st.tx = tx; st.ty = ty; st.nitems = nitems; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_full[s]);                     // + the TMA's tx bytes => phase completes
+        }
+        return;
+    }
+
+    // ===================================== consumer warps =====================================
+    const int cw = warp;
+    const int lx = lane & 3, ly = lane >> 2;
+    const float halfWc = 0.5f * Wc_f, halfHc = 0.5f * Hc_f;
+    const float gscale = (p.kind == SFH_LOSS_MSE ? 2.0f : 1.0f) * p.invN;
+    const float ncf = (float)p.nc;
+    for (int it = 0;; ++it) {
+        const int s = it % kPStages;
+        mbar_wait(&s_full[s], (it / kPStages) & 1);
+        const PStage& st = s_stage[s];
+        const int nitems = st.nitems;
+        if (nitems < 0) break;
+        const int b = st.b, tx = st.tx, band0 = st.ty * (8 * kPR);
+        const long long* s_gt = reinterpret_cast<const long long*>(s_dyn + (size_t)s * kPTileBytes);
+        Homog Hm;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Hm.h[k] = st.theta[k];
+        GradAcc acc;
+        acc.zero();
+        float loss_sum = 0.f;
+#define SFH_PIX_OK(j) (FT || (row_ok && col + (j) < W))
+#pragma unroll 1
+        for (int q = cw; q < nitems; q += kPCons) {
+            const unsigned item = st.items[q];
+            const int pr = (item & 0xffu) >> 3, pk = item & 7u, pc = (int)(item >> 8) - 1;
+            const int row = band0 + pr * 8 + ly;
+            const int col = tx * kTileW + pk * kPatchW + lx * 4;
+            const bool row_ok = FT || row < H;
+            const int rowc = FT ? row : min(row, H - 1);
+            const bool vec = FT || (p.vec4 && row_ok && col + 3 < W);
+            const size_t rowbase = ((size_t)b * H + rowc) * W + col;
+            const longlong2* sp2 = reinterpret_cast<const longlong2*>(s_gt + (pr * 8 + ly) * kTileW + pk * kPatchW + lx * 4);
+            const longlong2 glo = sp2[0], ghi = sp2[1];                 // zero-filled outside the image by TMA
+            const float gf[4] = {(float)(int)glo.x, (float)(int)glo.y, (float)(int)ghi.x, (float)(int)ghi.y};
+            float tgt[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tgt[j] = p.nc_pow2 ? __fmul_rn(gf[j], p.inv_nc) : __fdiv_rn(gf[j], ncf);
+
+            if (pc >= 0) {                                              // edge-free patch
+                const float cval = taps.class_value(pc);
+                if (p.out_f) {
+                    if (vec) __stcs((float4*)(p.out_f + rowbase), make_float4(cval, cval, cval, cval));
+                    else
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_f[rowbase + j] = cval;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d = cval - tgt[j];
+                    float l = (p.kind == SFH_LOSS_MSE || fabsf(d) < 1.0f) ? d * d : 2.0f * fabsf(d) - 1.0f;
+                    if (!SFH_PIX_OK(j)) l = 0.f;
+                    loss_sum += l;
+                }
+                continue;
+            }
+            // per-pixel path
+            const float v = p.ys ? __ldg(p.ys + rowc) : mesh_coord(rowc, H);
+            float u[4];
+            if (FT && p.xs) {
+                const float4 u4 = __ldg(reinterpret_cast<const float4*>(p.xs + col));
+                u[0] = u4.x; u[1] = u4.y; u[2] = u4.z; u[3] = u4.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int cx = min(col + j, W - 1);
+                    u[j] = p.xs ? __ldg(p.xs + cx) : mesh_coord(cx, W);
+                }
+            }
+            Pix px[4];
+            TapVals t[4];
+            float o[4], g[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                px[j] = pixel_geom<SFH_MODE_BILINEAR>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]),
+                                                      __fmul_rn(u[j], Hm.h[6]), v, Wc_f, Hc_f);
+                t[j] = taps.fetch4(0, px[j].x0, px[j].y0);
+                o[j] = bilerp(px[j], t[j]);
+            }
+            if (p.out_f) {
+                if (vec) __stcs((float4*)(p.out_f + rowbase), make_float4(o[0], o[1], o[2], o[3]));
+                else
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_f[rowbase + j] = o[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float d = o[j] - tgt[j];
+                float l;
+                if (p.kind == SFH_LOSS_MSE || fabsf(d) < 1.0f) { l = d * d; g[j] = d; }
+                else { l = 2.0f * fabsf(d) - 1.0f; g[j] = d > 0.f ? 1.0f : -1.0f; }
+                if (!SFH_PIX_OK(j)) { l = 0.f; g[j] = 0.f; }
+                loss_sum += l;
+                g[j] *= gscale;
+            }
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (__any_sync(0xffffffffu, !t[j].uni)) {
+                    const float gix = ((t[j].b - t[j].a) * px[j].sy + (t[j].d - t[j].c) * px[j].ny) * g[j];
+                    const float giy = ((t[j].c - t[j].a) * px[j].ex + (t[j].d - t[j].b) * px[j].wx) * g[j];
+                    acc.add(px[j], gix, giy, halfWc, halfHc, u[j]);
+                    any = true;
+                }
+            }
+            if (any) acc.end_row(v);
+        }
+#undef SFH_PIX_OK
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s]);                        // stage may be refilled
+
+        // ---- flush this warp's sums for the tile into its fixed slot, ticket on the sample ----
+        if (p.kind != SFH_LOSS_MSE) loss_sum *= 0.5f;
+        float vals[16];
+        vals[0] = loss_sum;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) vals[1 + k] = acc.a[k];
+#pragma unroll
+        for (int k = 10; k < 16; ++k) vals[k] = 0.f;
+        const float tot = warp_reduce16(vals, lane);
+        const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        const int tile_in_sample = st.ty * tiles_x + tx;
+        const int nslots = tiles_per_sample * kPCons;
+        float* slot = p.partials + ((size_t)b * nslots + (size_t)tile_in_sample * kPCons + cw) * kNPart;
+        if (!(lane & 1) && idx < kNPart) __stcg(slot + idx, tot);
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) last = (ticket_release(p.counters + b) == nslots - 1);
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) continue;
+
+        // ---- this warp took the sample's last ticket: fixed-order fp64 sum of all its slots ----
+        __threadfence();
+        double sum[kNPart];
+#pragma unroll
+        for (int k = 0; k < kNPart; ++k) sum[k] = 0.0;
+        const float* base = p.partials + (size_t)b * nslots * kNPart;
+        for (int q = lane; q < nslots; q += 32) {
+            const float4* r4 = reinterpret_cast<const float4*>(base + (size_t)q * kNPart);
+            const float4 a0 = __ldcg(r4), a1 = __ldcg(r4 + 1), a2 = __ldcg(r4 + 2);
+            sum[0] += a0.x; sum[1] += a0.y; sum[2] += a0.z; sum[3] += a0.w;
+            sum[4] += a1.x; sum[5] += a1.y; sum[6] += a1.z; sum[7] += a1.w;
+            sum[8] += a2.x; sum[9] += a2.y; sum[10] += a2.z; sum[11] += a2.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) sum[k] = warp_sum(sum[k]);
+        const double Lb = sum[0] / ((double)H * (double)W);
+        if (lane == 0) p.Lb[b] = (float)Lb;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) if (lane == k) p.J[9 * b + k] = (float)sum[1 + k];
+        if (p.loss_out) {
+            const int B = p.B;
+            double w_eff = 1.0;
+            if (p.weights) {
+                if (p.w_outer) {
+                    double sw = 0.0;
+                    for (int i = lane; i < B; i += 32)
+                        sw += p.w_f64 ? ((const double*)p.weights)[i] : (double)((const float*)p.weights)[i];
+                    w_eff = warp_sum(sw) / (double)B;
+                } else {
+                    w_eff = p.w_f64 ? ((const double*)p.weights)[b] : (double)((const float*)p.weights)[b];
+                }
+            }
+            const bool rep = p.poi.gt_poi != nullptr;
+            const double cr = (double)p.rec_lambda * w_eff, cp = (double)p.reproj_lambda;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                if (lane == k) {
+                    const double Kk = rep ? (double)__ldcg(p.poi.K + 9 * b + k) : 0.0;
+                    p.dtheta_total[9 * b + k] = (float)((cr * sum[1 + k] + cp * Kk) / (double)B);
+                }
+            }
+            int last2 = 0;
+            if (lane == 0) {
+                const double Rv = rep ? (double)__ldcg(p.poi.Rb + b) : 0.0;
+                __stcg(p.contrib + b, cr * Lb + cp * Rv);
+                last2 = (ticket_release(p.counters + B) == B - 1);
+            }
+            last2 = __shfl_sync(0xffffffffu, last2, 0);
+            if (last2) {
+                __threadfence();
+                double sacc = 0.0;
+                for (int i = lane; i < B; i += 32) sacc += __ldcg(p.contrib + i);
+                sacc = warp_sum(sacc);
+                if (lane == 0) { *p.loss_out = (float)(sacc / (double)B); p.counters[B] = 0; }
+            }
+        }
+        if (lane == 0) p.counters[b] = 0;
+    }
+}
+
 // Consistency score for logits sizes the fused pass does not cover (any h,w): reads the int32
 // mask back (L2-hot) with upsample_nearest's index rule.  models/reconstructor.py:230-238.
 __global__ void __launch_bounds__(kThreads) k_consistency_generic(const int32_t* mask, const float* logits,
@@ -774,8 +1127,8 @@ static inline bool aligned16(const void* q) { return ((uintptr_t)q & 15u) == 0; 
 static int setup_ws(FusedParams& p, void* ws, int64_t ws_bytes) {
     const int64_t need = sfh_workspace_bytes(p.B, p.H, p.W);
     if (!ws || ws_bytes < need) return SFH_E_WS;
-    p.counters = (int*)ws;                                             // [B+1]
-    p.contrib = (double*)((char*)ws + align_up((int64_t)(p.B + 1) * 4, 256));   // [B]
+    p.counters = (int*)ws;                                             // [B+3]: samples, batch, tile ticket, done
+    p.contrib = (double*)((char*)ws + align_up((int64_t)(p.B + 3) * 4, 256));   // [B]
     p.partials = (float*)((char*)p.contrib + align_up((int64_t)p.B * 8, 256));
     return 0;
 }
@@ -809,6 +1162,39 @@ static int launch_fused(const FusedParams& p, cudaStream_t st) {
         case SFH_TMPL_F32: return launch_fmt<SFH_TMPL_F32, MODE, EPI>(p, grid, dyn, ft, st);
         case SFH_TMPL_Q2:  return launch_fmt<SFH_TMPL_Q2, MODE, EPI>(p, grid, dyn, ft, st);
         case SFH_TMPL_Q4:  return launch_fmt<SFH_TMPL_Q4, MODE, EPI>(p, grid, dyn, ft, st);
+        default: return SFH_E_BADFMT;
+    }
+}
+
+template <int FMT>
+static int launch_persistent_fmt(const FusedParams& p, bool ft, int ctas, cudaStream_t st) {
+    auto kf = k_train_persistent<FMT, true>;
+    auto kg = k_train_persistent<FMT, false>;
+    const size_t dyn = (size_t)kPStages * kPTileBytes;
+    static bool raised = false;
+    if (!raised) {
+        cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        raised = true;
+    }
+    if (ft) kf<<<ctas, kPThreads, dyn, st>>>(p);
+    else    kg<<<ctas, kPThreads, dyn, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+static int launch_persistent(const FusedParams& p, cudaStream_t st) {
+    static const int sms = [] {
+        int dev = 0, n = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n;
+    }();
+    const int total = p.ntiles * p.B;
+    const int ctas = total < sms ? total : sms;
+    const bool ft = p.vec4 && (p.W % kTileW == 0) && (p.H % 8 == 0) && (!p.xs || (((uintptr_t)p.xs & 15u) == 0));
+    switch (p.t.fmt) {
+        case SFH_TMPL_F32: return launch_persistent_fmt<SFH_TMPL_F32>(p, ft, ctas, st);
+        case SFH_TMPL_Q2:  return launch_persistent_fmt<SFH_TMPL_Q2>(p, ft, ctas, st);
+        case SFH_TMPL_Q4:  return launch_persistent_fmt<SFH_TMPL_Q4>(p, ft, ctas, st);
         default: return SFH_E_BADFMT;
     }
 }
@@ -869,8 +1255,11 @@ const char* sfh_error_string(int code) {
 
 int64_t sfh_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
-    const int64_t ntiles = (int64_t)((W + kTileW - 1) / kTileW) * ((H + kWarps - 1) / kWarps);   // R = 1 upper bound
-    return align_up((int64_t)(B + 1) * 4, 256) + align_up((int64_t)B * 8, 256) + (int64_t)B * ntiles * kNPart * 4;
+    const int64_t tx = (W + kTileW - 1) / kTileW;
+    const int64_t ntiles = tx * ((H + kWarps - 1) / kWarps);                      // k_fused, R = 1 upper bound
+    const int64_t nslots = tx * ((H + 8 * kPR - 1) / (8 * kPR)) * kPCons;         // k_train_persistent
+    const int64_t n = ntiles > nslots ? ntiles : nslots;
+    return align_up((int64_t)(B + 3) * 4, 256) + align_up((int64_t)B * 8, 256) + (int64_t)B * n * kNPart * 4;
 }
 
 int sfh_template_pack(const float* tmpl, int Hc, int Wc, const float* palette_host, int n_palette,
@@ -957,6 +1346,17 @@ int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* a
     if (p.rows_per_warp > 8) {               // keep the staged gt tile <= 64 KiB per CTA
         p.rows_per_warp = 8;
         p.ntiles = ((a->W + kTileW - 1) / kTileW) * ((a->H + 63) / 64);
+    }
+    static const bool no_persist = getenv("SFH_NO_PERSISTENT") != nullptr;
+    if (!no_persist) {
+        // persistent warp-specialised kernel: 128 x 64 tiles, one CTA per SM
+        FusedParams q = p;
+        q.rows_per_warp = kPR;
+        q.ntiles = ((a->W + kTileW - 1) / kTileW) * ((a->H + 8 * kPR - 1) / (8 * kPR));
+        if (make_gt_map(q)) {
+            q.use_tma = 1;
+            return launch_persistent(q, (cudaStream_t)stream);
+        }
     }
     p.use_tma = make_gt_map(p) ? 1 : 0;
     return launch_fused<SFH_MODE_BILINEAR, kEpiLoss>(p, (cudaStream_t)stream);

@@ -42,9 +42,9 @@ def test_abi_metadata_and_argument_errors_without_gpu():
     assert b"sm_100a" in l.sfh_build_info()
     assert l.sfh_error_string(0) == b"success"
     assert b"workspace" in l.sfh_error_string(-4)
-    # workspace size is pure host arithmetic: B+1 tickets and B doubles (each 256-aligned)
-    # + 12 floats per CTA partial, sized for the smallest tile (128 x 8 rows)
-    assert l.sfh_workspace_bytes(64, 360, 640) == 512 + 512 + 64 * 5 * 45 * 12 * 4
+    # workspace size is pure host arithmetic: B+3 tickets and B doubles (each 256-aligned)
+    # + 12 floats per partial slot: max(one per 128x8 tile, 16 per 128x64 tile)
+    assert l.sfh_workspace_bytes(64, 360, 640) == 512 + 512 + 64 * max(5 * 45, 5 * 6 * 16) * 12 * 4
     assert l.sfh_workspace_bytes(0, 360, 640) == 0
     # argument validation happens before any CUDA call
     assert l.sfh_warp_fwd(None, None, None, None, 1, 1, 1, 0, None, None) < 0
