@@ -1110,14 +1110,15 @@ static void fill_common(FusedParams& p, const float* theta, const sfh_template* 
     memset(&p, 0, sizeof(p));
     p.theta = theta; p.xs = xs; p.ys = ys; p.t = *t;
     p.B = B; p.H = H; p.W = W;
-    // rows per warp: the largest R in {16,8,4,2,1} that still leaves >= 8 waves of CTAs
-    // (3 CTAs/SM x 148 SMs); bigger tiles amortise the per-CTA prologue and reduction.
+    // bands per CTA: the largest R in {16,8,4,2,1} that still leaves >= 4 waves of CTAs
+    // (3 CTAs/SM x 148 SMs); bigger tiles amortise the per-CTA prologue and reduction
+    // (measured on B200, C2: R=2 95 us, R=4 70 us, R=8 61 us).
     static const int forced = [] { const char* e = getenv("SFH_ROWS_PER_WARP"); return e ? atoi(e) : 0; }();
     const int tiles_x = (W + kTileW - 1) / kTileW;
     int R = 16;
     if (forced > 0) R = forced;
     else
-        while (R > 1 && (int64_t)tiles_x * ((H + kWarps * R - 1) / (kWarps * R)) * B < 8 * 3 * 148) R >>= 1;
+        while (R > 1 && (int64_t)tiles_x * ((H + kWarps * R - 1) / (kWarps * R)) * B < 4 * 3 * 148) R >>= 1;
     p.rows_per_warp = R;
     p.ntiles = tiles_x * ((H + kWarps * R - 1) / (kWarps * R));
 }
@@ -1347,8 +1348,10 @@ int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* a
         p.rows_per_warp = 8;
         p.ntiles = ((a->W + kTileW - 1) / kTileW) * ((a->H + 63) / 64);
     }
-    static const bool no_persist = getenv("SFH_NO_PERSISTENT") != nullptr;
-    if (!no_persist) {
+    // experimental persistent warp-specialised variant (opt-in until it beats k_fused: with 3 x 64 KiB
+    // gt stages the L1 carve-out left for the template taps is too small — see DESIGN.md §4)
+    static const bool persist = getenv("SFH_PERSISTENT") != nullptr;
+    if (persist) {
         // persistent warp-specialised kernel: 128 x 64 tiles, one CTA per SM
         FusedParams q = p;
         q.rows_per_warp = kPR;

@@ -387,14 +387,16 @@ def test_edge_free_patch_shortcut_matches_exact_mode(W, H, B, fam, name):
         re_ = ex.train_step(th, cu(gt), w, kind)
         rf = fa.train_step(th, cu(gt), w, kind)
         np.testing.assert_allclose(rf["rec_per_sample"].cpu().numpy(), re_["rec_per_sample"].cpu().numpy(), rtol=1e-6)
-        assert torch.equal(rf["dtheta"], re_["dtheta"])
+        # same pixels contribute (edge-free patches add exact zeros); only the order in which
+        # patches are dealt to warps differs between the two modes
+        assert relnorm(rf["dtheta"].cpu().numpy(), re_["dtheta"].cpu().numpy()).max() <= 2e-6
         assert float((rf["warp_mask"] - re_["warp_mask"]).abs().max()) <= 2.5e-7
     # generic backward: patches without an edge are skipped entirely
     go = torch.randn(B, H, W, generator=torch.Generator().manual_seed(3)).to(DEV)
     t1, t2 = th.clone().requires_grad_(True), th.clone().requires_grad_(True)
     ex.warp(t1).backward(go)
     fa.warp(t2).backward(go)
-    assert torch.equal(t1.grad, t2.grad)
+    assert relnorm(t1.grad.cpu().numpy(), t2.grad.cpu().numpy()).max() <= 2e-6
     # nearest (always uses the shortcut): bit-exact against the oracle, incl. the int32 predict mask
     stn = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, warp_with_nearest=True, **kw)
     refn = co.warp_fwd(th.cpu().numpy(), tmpl.numpy(), H, W, "nearest")[:, 0]
