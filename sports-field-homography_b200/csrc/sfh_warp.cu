@@ -650,31 +650,34 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------
-// Persistent, warp-specialised training kernel (kEpiLoss with a TMA-staged gt tile).
+// Persistent, warp-specialised training kernel (kEpiLoss with TMA-staged gt tiles).
 //
-// One CTA per SM: 1 producer warp + 16 consumer warps, a 3-stage ring of 128 x 64 px tiles.
-//   producer   takes the next tile from a global ticket, issues ONE TMA tensor load for its int64
-//              gt tile (64 KiB), and while that is in flight loads theta, classifies the tile's 64
-//              patches against the edge summed-area table and writes the edge-first patch list
-//              into the stage; arrives on the stage's `full` mbarrier (TMA completes the tx count).
-//   consumers  wait on `full`, each takes patches cw, cw+16, ... of the list (per-pixel path for
-//              edge patches, constant path otherwise), flush their 10 sums for the tile with a
-//              16-value shuffle butterfly into a fixed slot, take a release ticket on the sample,
-//              and arrive on the stage's `empty` mbarrier.  No __syncthreads in the steady state.
-// The warp that takes a sample's last ticket sums that sample's slots in fixed order in fp64
-// (results do not depend on which SM processed which tile) and runs the optional batch combine.
+// One CTA per SM: 1 producer warp + 15 consumer warps, a 4-stage ring of 128 x 32 px tiles.
+//   producer   takes chunks of consecutive tiles of one sample from a global ticket; per tile it
+//              issues ONE TMA tensor load for the int64 gt tile (32 KiB) and, while that is in
+//              flight, loads theta, classifies the tile's 32 patches against the edge summed-area
+//              table and writes the edge-first patch list into the stage; it then arrives on the
+//              stage's `full` mbarrier (the TMA completes the tx count of the same barrier).
+//   consumers  wait on `full`, take patches of the list round-robin (per-pixel path for edge
+//              patches, constant path otherwise), arrive on the stage's `empty` mbarrier, and keep
+//              their 10 sums in registers for the whole chunk; at a chunk boundary a 16-value
+//              shuffle butterfly writes them to the fixed slot (sample, chunk, warp).
+// No __syncthreads, no atomics and no fences in the steady state.  k_train_finalize then adds every
+// sample's slots in fixed order in fp64 (results do not depend on which SM ran which chunk) and
+// applies the optional weighting / batch mean / total dtheta.
 // ------------------------------------------------------------------------------------------
-constexpr int kPCons = 16;                       // consumer warps
-constexpr int kPThreads = 32 * (kPCons + 1);
-constexpr int kPStages = 3;
-constexpr int kPR = 8;                           // bands per tile
-constexpr int kPItems = kPR * kWarps;            // 64 patches per tile
+constexpr int kPCons = 15;                       // consumer warps
+constexpr int kPThreads = 32 * (kPCons + 1);     // 512: 4 warps per SM sub-partition
+constexpr int kPStages = 4;
+constexpr int kPR = 4;                           // bands per tile: 128 x 32 px
+constexpr int kPItems = kPR * kWarps;            // 32 patches per tile
 constexpr int kPTileBytes = kPR * 8 * kTileW * 8;
+constexpr int kPChunk = 6;                       // tiles per chunk (consecutive tiles of one sample)
 
 struct PStage {
     unsigned short items[kPItems];
     float theta[9];
-    int b, tx, ty, nitems;                       // nitems < 0: no more tiles
+    int b, tx, ty, nitems, slot;                 // nitems < 0: no more tiles; slot >= 0: last tile of its chunk
 };
 
 __device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {
@@ -696,11 +699,10 @@ __global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
     const int tiles_x = (W + kTileW - 1) / kTileW;
-    const int tiles_y = (H + 8 * kPR - 1) / (8 * kPR);
-    const int tiles_per_sample = tiles_x * tiles_y;
-    const int total_tiles = tiles_per_sample * p.B;
-    int* tile_ctr = p.counters + p.B + 1;
-    int* done_ctr = p.counters + p.B + 2;
+    const int tiles_per_sample = tiles_x * ((H + 8 * kPR - 1) / (8 * kPR));
+    const int chunks_per_sample = (tiles_per_sample + kPChunk - 1) / kPChunk;
+    const int total_chunks = chunks_per_sample * p.B;
+    int* chunk_ctr = p.counters + p.B + 1;
 
     Taps<FMT> taps;
     if (threadIdx.x < kThreads) taps.build_tables(p.t, s_tab);         // 256-entry LUT: first 256 threads
@@ -718,123 +720,125 @@ __global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_
 
     if (warp == kPCons) {
         // =================================== producer warp ===================================
-        for (int it = 0;; ++it) {
-            const int s = it % kPStages;
-            mbar_wait(&s_empty[s], ((it / kPStages) & 1) ^ 1);          // consumers released this stage
-            int t = 0;
-            if (lane == 0) t = atomicAdd(tile_ctr, 1);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            PStage& st = s_stage[s];
-            if (t >= total_tiles) {
-                if (lane == 0) { st.nitems = -1; }
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&s_full[s]);
-                    // the last CTA to run out of tiles re-zeroes the tile ticket for the next launch
-                    if (atomicAdd(done_ctr, 1) == (int)gridDim.x - 1) { *tile_ctr = 0; *done_ctr = 0; }
-                }
-                break;
-            }
-            const int b = t / tiles_per_sample, rem = t - b * tiles_per_sample;
-            const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-            const int band0 = ty * (8 * kPR);
-            const int nitems = min(kPR, (H - band0 + 7) >> 3) * kWarps;
-            if (lane == 0) {
-                mbar_expect_tx_only(&s_full[s], (uint32_t)kPTileBytes);
-                tma_load_3d(s_dyn + (size_t)s * kPTileBytes, &p.gt_map, tx * kTileW, band0, b, &s_full[s]);
-            }
+        int it = 0;
+        int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(chunk_ctr, 1);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        while (chunk < total_chunks) {
+            int next_chunk = 0;
+            if (lane == 0) next_chunk = atomicAdd(chunk_ctr, 1);        // prefetched; consumed after this chunk
+            const int b = chunk / chunks_per_sample, cis = chunk - b * chunks_per_sample;
+            const int t0 = cis * kPChunk, t1 = min(t0 + kPChunk, tiles_per_sample);
             Homog Hm;
             Hm.load(p.theta + 9 * b);
-            if (rem == 0 && p.poi.court_poi) poi_warp(p.poi, b, lane);  // the sample's court points (fp64)
-            if (classify) {
-                for (int g = lane; g < (kWarps + 1) * (kPR + 1); g += 32) {
-                    const int r = g / (kWarps + 1), k = g - r * (kWarps + 1);
-                    const int grow = min(band0 + 8 * r, H - 1), gcol = min(tx * kTileW + kPatchW * k, W - 1);
-                    const float gu = p.xs ? __ldg(p.xs + gcol) : mesh_coord(gcol, W);
-                    const float gv = p.ys ? __ldg(p.ys + grow) : mesh_coord(grow, H);
-                    const Flow f = flow_at(Hm, __fmul_rn(gu, Hm.h[0]), __fmul_rn(gu, Hm.h[3]), __fmul_rn(gu, Hm.h[6]), gv);
-                    s_gx[r][k] = __fmul_rn(__fmaf_rn(__fadd_rn(f.x, 1.0f), Wc_f, -1.0f), 0.5f);
-                    s_gy[r][k] = __fmul_rn(__fmaf_rn(__fadd_rn(f.y, 1.0f), Hc_f, -1.0f), 0.5f);
-                    s_gz[r][k] = f.zok ? __fdividef(1.0f, f.s) : __int_as_float(0x7fc00000);
+            if (cis == 0 && p.poi.court_poi) poi_warp(p.poi, b, lane);  // the sample's court points (fp64)
+            for (int rem = t0; rem < t1; ++rem, ++it) {
+                const int s = it % kPStages;
+                mbar_wait(&s_empty[s], ((it / kPStages) & 1) ^ 1);      // consumers released this stage
+                PStage& st = s_stage[s];
+                const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+                const int band0 = ty * (8 * kPR);
+                const int nitems = min(kPR, (H - band0 + 7) >> 3) * kWarps;
+                if (lane == 0) {
+                    mbar_expect_tx_only(&s_full[s], (uint32_t)kPTileBytes);
+                    tma_load_3d(s_dyn + (size_t)s * kPTileBytes, &p.gt_map, tx * kTileW, band0, b, &s_full[s]);
+                }
+                int cls = -1;
+                if (classify) {
+                    for (int g = lane; g < (kWarps + 1) * (kPR + 1); g += 32) {
+                        const int r = g / (kWarps + 1), k = g - r * (kWarps + 1);
+                        const int grow = min(band0 + 8 * r, H - 1), gcol = min(tx * kTileW + kPatchW * k, W - 1);
+                        const float gu = p.xs ? __ldg(p.xs + gcol) : mesh_coord(gcol, W);
+                        const float gv = p.ys ? __ldg(p.ys + grow) : mesh_coord(grow, H);
+                        const Flow f = flow_at(Hm, __fmul_rn(gu, Hm.h[0]), __fmul_rn(gu, Hm.h[3]), __fmul_rn(gu, Hm.h[6]), gv);
+                        s_gx[r][k] = __fmul_rn(__fmaf_rn(__fadd_rn(f.x, 1.0f), Wc_f, -1.0f), 0.5f);
+                        s_gy[r][k] = __fmul_rn(__fmaf_rn(__fadd_rn(f.y, 1.0f), Hc_f, -1.0f), 0.5f);
+                        s_gz[r][k] = f.zok ? __fdividef(1.0f, f.s) : __int_as_float(0x7fc00000);
+                    }
+                    __syncwarp();
+                    if (lane < nitems) {
+                        const int r = lane / kWarps, k = lane % kWarps;
+                        const float x00 = s_gx[r][k], x01 = s_gx[r][k + 1], x10 = s_gx[r + 1][k], x11 = s_gx[r + 1][k + 1];
+                        const float y00 = s_gy[r][k], y01 = s_gy[r][k + 1], y10 = s_gy[r + 1][k], y11 = s_gy[r + 1][k + 1];
+                        const float z00 = s_gz[r][k], z01 = s_gz[r][k + 1], z10 = s_gz[r + 1][k], z11 = s_gz[r + 1][k + 1];
+                        const float xmin = fminf(fminf(x00, x01), fminf(x10, x11)), xmax = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11));
+                        const float ymin = fminf(fminf(y00, y01), fminf(y10, y11)), ymax = fmaxf(fmaxf(y00, y01), fmaxf(y10, y11));
+                        const bool zpos = (z00 > 0.f) & (z01 > 0.f) & (z10 > 0.f) & (z11 > 0.f);
+                        const bool zneg = (z00 < 0.f) & (z01 < 0.f) & (z10 < 0.f) & (z11 < 0.f);
+                        const bool fin = (x00 == x00) & (x01 == x01) & (x10 == x10) & (x11 == x11) &
+                                         (y00 == y00) & (y01 == y01) & (y10 == y10) & (y11 == y11) &
+                                         (xmin > -1e9f) & (xmax < 1e9f) & (ymin > -1e9f) & (ymax < 1e9f);
+                        if ((zpos | zneg) & fin) {
+                            const int wmax = p.t.width + 1, hmax = p.t.height + 1;
+                            const int i0 = min(max(__float2int_rd(xmin - kBoxMargin) + 1, 0), wmax);
+                            const int i1 = min(max(__float2int_rd(xmax + kBoxMargin) + 2, 0), wmax);
+                            const int j0 = min(max(__float2int_rd(ymin - kBoxMargin) + 1, 0), hmax);
+                            const int j1 = min(max(__float2int_rd(ymax + kBoxMargin) + 2, 0), hmax);
+                            const unsigned* S = p.t.sat;
+                            const int sp = p.t.sat_pitch;
+                            const unsigned ec = taps.entry_class(i0, j0);
+                            const unsigned cnt = __ldg(S + (j1 + 1) * sp + (i1 + 1)) - __ldg(S + j0 * sp + (i1 + 1))
+                                               - __ldg(S + (j1 + 1) * sp + i0) + __ldg(S + j0 * sp + i0);
+                            if (cnt == 0u) cls = (int)ec;
+                        }
+                    }
+                    __syncwarp();                                       // scratch is reused by the next tile
+                }
+                // edge-first patch list: one ballot gives every rank
+                const bool e = (lane < nitems) && cls < 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, e);
+                if (lane < nitems) {
+                    const int before = __popc(bal & ((1u << lane) - 1u)), total = __popc(bal);
+                    st.items[e ? before : total + (lane - before)] = (unsigned short)(lane | ((cls + 1) << 8));
+                }
+                if (lane < 9) st.theta[lane] = Hm.h[0] * 0.f + __ldg(p.theta + 9 * b + lane);
+                if (lane == 0) {
+                    st.b = b; st.tx = tx; st.ty = ty; st.nitems = nitems;
+                    st.slot = (rem == t1 - 1) ? (b * chunks_per_sample + cis) : -1;
                 }
                 __syncwarp();
+                if (lane == 0) mbar_arrive(&s_full[s]);                 // + the TMA's tx bytes => phase completes
             }
-            int cls[2] = {-1, -1};
-            if (classify) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int id = lane + 32 * h;
-                    if (id >= nitems) continue;
-                    const int r = id / kWarps, k = id % kWarps;
-                    const float x00 = s_gx[r][k], x01 = s_gx[r][k + 1], x10 = s_gx[r + 1][k], x11 = s_gx[r + 1][k + 1];
-                    const float y00 = s_gy[r][k], y01 = s_gy[r][k + 1], y10 = s_gy[r + 1][k], y11 = s_gy[r + 1][k + 1];
-                    const float z00 = s_gz[r][k], z01 = s_gz[r][k + 1], z10 = s_gz[r + 1][k], z11 = s_gz[r + 1][k + 1];
-                    const float xmin = fminf(fminf(x00, x01), fminf(x10, x11)), xmax = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11));
-                    const float ymin = fminf(fminf(y00, y01), fminf(y10, y11)), ymax = fmaxf(fmaxf(y00, y01), fmaxf(y10, y11));
-                    const bool zpos = (z00 > 0.f) & (z01 > 0.f) & (z10 > 0.f) & (z11 > 0.f);
-                    const bool zneg = (z00 < 0.f) & (z01 < 0.f) & (z10 < 0.f) & (z11 < 0.f);
-                    const bool fin = (x00 == x00) & (x01 == x01) & (x10 == x10) & (x11 == x11) &
-                                     (y00 == y00) & (y01 == y01) & (y10 == y10) & (y11 == y11) &
-                                     (xmin > -1e9f) & (xmax < 1e9f) & (ymin > -1e9f) & (ymax < 1e9f);
-                    if ((zpos | zneg) & fin) {
-                        const int wmax = p.t.width + 1, hmax = p.t.height + 1;
-                        const int i0 = min(max(__float2int_rd(xmin - kBoxMargin) + 1, 0), wmax);
-                        const int i1 = min(max(__float2int_rd(xmax + kBoxMargin) + 2, 0), wmax);
-                        const int j0 = min(max(__float2int_rd(ymin - kBoxMargin) + 1, 0), hmax);
-                        const int j1 = min(max(__float2int_rd(ymax + kBoxMargin) + 2, 0), hmax);
-                        const unsigned* S = p.t.sat;
-                        const int sp = p.t.sat_pitch;
-                        const unsigned ec = taps.entry_class(i0, j0);
-                        const unsigned cnt = __ldg(S + (j1 + 1) * sp + (i1 + 1)) - __ldg(S + j0 * sp + (i1 + 1))
-                                           - __ldg(S + (j1 + 1) * sp + i0) + __ldg(S + j0 * sp + i0);
-                        if (cnt == 0u) cls[h] = (int)ec;
-                    }
-                }
-            }
-            // edge-first patch list (single warp: two ballots give every rank)
-            const bool e0 = (lane < nitems) && cls[0] < 0, e1 = (lane + 32 < nitems) && cls[1] < 0;
-            const unsigned b0 = __ballot_sync(0xffffffffu, e0), b1 = __ballot_sync(0xffffffffu, e1);
-            const unsigned lt = (1u << lane) - 1u;
-            const int n0 = __popc(b0), total = n0 + __popc(b1);
-            if (lane < nitems) {
-                const int before = __popc(b0 & lt);
-                st.items[e0 ? before : total + (lane - before)] = (unsigned short)(lane | ((cls[0] + 1) << 8));
-            }
-            if (lane + 32 < nitems) {
-                const int before = n0 + __popc(b1 & lt);
-                st.items[e1 ? before : total + (lane + 32 - before)] = (unsigned short)((lane + 32) | ((cls[1] + 1) << 8));
-            }
-            if (lane < 9) st.theta[lane] = Hm.h[0] * 0.f + __ldg(p.theta + 9 * b + lane);
-            if (lane == 0) { st.b = b; st.tx = tx; st.ty = ty; st.nitems = nitems; }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_full[s]);                     // + the TMA's tx bytes => phase completes
+            chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
         }
+        // no more work: poison the next stage so the consumers leave
+        const int s = it % kPStages;
+        mbar_wait(&s_empty[s], ((it / kPStages) & 1) ^ 1);
+        if (lane == 0) { s_stage[s].nitems = -1; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_full[s]);
         return;
     }
 
     // ===================================== consumer warps =====================================
     const int cw = warp;
     const int lx = lane & 3, ly = lane >> 2;
+    const int lane_px = ly * kTileW + lx * 4;                           // lane's offset inside a patch row block
     const float halfWc = 0.5f * Wc_f, halfHc = 0.5f * Hc_f;
     const float gscale = (p.kind == SFH_LOSS_MSE ? 2.0f : 1.0f) * p.invN;
     const float ncf = (float)p.nc;
+    GradAcc acc;
+    acc.zero();
+    float loss_sum = 0.f;
     for (int it = 0;; ++it) {
         const int s = it % kPStages;
         mbar_wait(&s_full[s], (it / kPStages) & 1);
         const PStage& st = s_stage[s];
         const int nitems = st.nitems;
         if (nitems < 0) break;
-        const int b = st.b, tx = st.tx, band0 = st.ty * (8 * kPR);
+        const int b = st.b, tx = st.tx, band0 = st.ty * (8 * kPR), slot = st.slot;
         const long long* s_gt = reinterpret_cast<const long long*>(s_dyn + (size_t)s * kPTileBytes);
+        const size_t base_b = (size_t)b * H * W;
+        float* outb = p.out_f ? p.out_f + base_b : nullptr;
         Homog Hm;
 #pragma unroll
         for (int k = 0; k < 9; ++k) Hm.h[k] = st.theta[k];
-        GradAcc acc;
-        acc.zero();
-        float loss_sum = 0.f;
 #define SFH_PIX_OK(j) (FT || (row_ok && col + (j) < W))
+        // rotate the starting patch with the tile index so the 32 % 15 remainder is shared out
+        int q = cw + (it % kPCons);
+        if (q >= kPCons) q -= kPCons;
 #pragma unroll 1
-        for (int q = cw; q < nitems; q += kPCons) {
+        for (; q < nitems; q += kPCons) {
             const unsigned item = st.items[q];
             const int pr = (item & 0xffu) >> 3, pk = item & 7u, pc = (int)(item >> 8) - 1;
             const int row = band0 + pr * 8 + ly;
@@ -842,8 +846,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_
             const bool row_ok = FT || row < H;
             const int rowc = FT ? row : min(row, H - 1);
             const bool vec = FT || (p.vec4 && row_ok && col + 3 < W);
-            const size_t rowbase = ((size_t)b * H + rowc) * W + col;
-            const longlong2* sp2 = reinterpret_cast<const longlong2*>(s_gt + (pr * 8 + ly) * kTileW + pk * kPatchW + lx * 4);
+            const int off = rowc * W + col;
+            const longlong2* sp2 = reinterpret_cast<const longlong2*>(s_gt + pr * (8 * kTileW) + pk * kPatchW + lane_px);
             const longlong2 glo = sp2[0], ghi = sp2[1];                 // zero-filled outside the image by TMA
             const float gf[4] = {(float)(int)glo.x, (float)(int)glo.y, (float)(int)ghi.x, (float)(int)ghi.y};
             float tgt[4];
@@ -852,11 +856,11 @@ __global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_
 
             if (pc >= 0) {                                              // edge-free patch
                 const float cval = taps.class_value(pc);
-                if (p.out_f) {
-                    if (vec) __stcs((float4*)(p.out_f + rowbase), make_float4(cval, cval, cval, cval));
+                if (outb) {
+                    if (vec) __stcs((float4*)(outb + off), make_float4(cval, cval, cval, cval));
                     else
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_f[rowbase + j] = cval;
+                        for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) outb[off + j] = cval;
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -890,11 +894,11 @@ __global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_
                 t[j] = taps.fetch4(0, px[j].x0, px[j].y0);
                 o[j] = bilerp(px[j], t[j]);
             }
-            if (p.out_f) {
-                if (vec) __stcs((float4*)(p.out_f + rowbase), make_float4(o[0], o[1], o[2], o[3]));
+            if (outb) {
+                if (vec) __stcs((float4*)(outb + off), make_float4(o[0], o[1], o[2], o[3]));
                 else
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_f[rowbase + j] = o[j];
+                    for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) outb[off + j] = o[j];
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -921,84 +925,88 @@ __global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_
 #undef SFH_PIX_OK
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[s]);                        // stage may be refilled
+        if (slot < 0) continue;
 
-        // ---- flush this warp's sums for the tile into its fixed slot, ticket on the sample ----
-        if (p.kind != SFH_LOSS_MSE) loss_sum *= 0.5f;
+        // ---- chunk boundary: this warp's sums go to the fixed slot (sample, chunk, warp) ----
         float vals[16];
-        vals[0] = loss_sum;
+        vals[0] = (p.kind != SFH_LOSS_MSE) ? 0.5f * loss_sum : loss_sum;
 #pragma unroll
         for (int k = 0; k < 9; ++k) vals[1 + k] = acc.a[k];
 #pragma unroll
         for (int k = 10; k < 16; ++k) vals[k] = 0.f;
         const float tot = warp_reduce16(vals, lane);
         const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-        const int tile_in_sample = st.ty * tiles_x + tx;
-        const int nslots = tiles_per_sample * kPCons;
-        float* slot = p.partials + ((size_t)b * nslots + (size_t)tile_in_sample * kPCons + cw) * kNPart;
-        if (!(lane & 1) && idx < kNPart) __stcg(slot + idx, tot);
-        __syncwarp();
-        int last = 0;
-        if (lane == 0) last = (ticket_release(p.counters + b) == nslots - 1);
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (!last) continue;
+        if (!(lane & 1) && idx < kNPart) p.partials[((size_t)slot * kPCons + cw) * kNPart + idx] = tot;
+        acc.zero();
+        loss_sum = 0.f;
+    }
+}
 
-        // ---- this warp took the sample's last ticket: fixed-order fp64 sum of all its slots ----
-        __threadfence();
-        double sum[kNPart];
-#pragma unroll
-        for (int k = 0; k < kNPart; ++k) sum[k] = 0.0;
-        const float* base = p.partials + (size_t)b * nslots * kNPart;
-        for (int q = lane; q < nslots; q += 32) {
-            const float4* r4 = reinterpret_cast<const float4*>(base + (size_t)q * kNPart);
-            const float4 a0 = __ldcg(r4), a1 = __ldcg(r4 + 1), a2 = __ldcg(r4 + 2);
-            sum[0] += a0.x; sum[1] += a0.y; sum[2] += a0.z; sum[3] += a0.w;
-            sum[4] += a1.x; sum[5] += a1.y; sum[6] += a1.z; sum[7] += a1.w;
-            sum[8] += a2.x; sum[9] += a2.y; sum[10] += a2.z; sum[11] += a2.w;
+// Second stage of the persistent path: one CTA per sample adds that sample's (chunk, warp) slots in
+// fixed order in fp64, then the optional weighting + batch mean + total dtheta (last CTA by ticket).
+__global__ void __launch_bounds__(kThreads) k_train_finalize(const __grid_constant__ FusedParams p) {
+    __shared__ double s_fin[kNPart][kFinGroup];
+    __shared__ double s_out[kNPart];
+    const int b = blockIdx.x, H = p.H, W = p.W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tiles_x = (W + kTileW - 1) / kTileW;
+    const int tiles_per_sample = tiles_x * ((H + 8 * kPR - 1) / (8 * kPR));
+    const int nslots = ((tiles_per_sample + kPChunk - 1) / kPChunk) * kPCons;
+    if (b == 0 && threadIdx.x == 0) p.counters[p.B + 1] = 0;           // chunk ticket for the next launch
+    {
+        const int k = threadIdx.x / kFinGroup, jj = threadIdx.x % kFinGroup;
+        if (k < kNPart) {
+            double s = 0.0;
+            const float* base = p.partials + (size_t)b * nslots * kNPart + k;
+            for (int t = jj; t < nslots; t += kFinGroup) s += (double)base[(size_t)t * kNPart];
+            s_fin[k][jj] = s;
         }
+    }
+    __syncthreads();
+    if (threadIdx.x < kNPart) {
+        const int k = threadIdx.x;
+        double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < 10; ++k) sum[k] = warp_sum(sum[k]);
-        const double Lb = sum[0] / ((double)H * (double)W);
-        if (lane == 0) p.Lb[b] = (float)Lb;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) if (lane == k) p.J[9 * b + k] = (float)sum[1 + k];
-        if (p.loss_out) {
-            const int B = p.B;
-            double w_eff = 1.0;
-            if (p.weights) {
-                if (p.w_outer) {
-                    double sw = 0.0;
-                    for (int i = lane; i < B; i += 32)
-                        sw += p.w_f64 ? ((const double*)p.weights)[i] : (double)((const float*)p.weights)[i];
-                    w_eff = warp_sum(sw) / (double)B;
-                } else {
-                    w_eff = p.w_f64 ? ((const double*)p.weights)[b] : (double)((const float*)p.weights)[b];
-                }
-            }
-            const bool rep = p.poi.gt_poi != nullptr;
-            const double cr = (double)p.rec_lambda * w_eff, cp = (double)p.reproj_lambda;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                if (lane == k) {
-                    const double Kk = rep ? (double)__ldcg(p.poi.K + 9 * b + k) : 0.0;
-                    p.dtheta_total[9 * b + k] = (float)((cr * sum[1 + k] + cp * Kk) / (double)B);
-                }
-            }
-            int last2 = 0;
-            if (lane == 0) {
-                const double Rv = rep ? (double)__ldcg(p.poi.Rb + b) : 0.0;
-                __stcg(p.contrib + b, cr * Lb + cp * Rv);
-                last2 = (ticket_release(p.counters + B) == B - 1);
-            }
-            last2 = __shfl_sync(0xffffffffu, last2, 0);
-            if (last2) {
-                __threadfence();
-                double sacc = 0.0;
-                for (int i = lane; i < B; i += 32) sacc += __ldcg(p.contrib + i);
-                sacc = warp_sum(sacc);
-                if (lane == 0) { *p.loss_out = (float)(sacc / (double)B); p.counters[B] = 0; }
+        for (int jj = 0; jj < kFinGroup; ++jj) s += s_fin[k][jj];
+        if (k == 0) { s = s / ((double)H * (double)W); p.Lb[b] = (float)s; }
+        else if (k <= 9) p.J[9 * b + k - 1] = (float)s;
+        s_out[k] = s;
+    }
+    if (!p.loss_out) return;
+    __syncthreads();
+    if (warp == 0) {
+        const int B = p.B;
+        double w_eff = 1.0;
+        if (p.weights) {
+            if (p.w_outer) {
+                double sw = 0.0;
+                for (int i = lane; i < B; i += 32)
+                    sw += p.w_f64 ? ((const double*)p.weights)[i] : (double)((const float*)p.weights)[i];
+                w_eff = warp_sum(sw) / (double)B;
+            } else {
+                w_eff = p.w_f64 ? ((const double*)p.weights)[b] : (double)((const float*)p.weights)[b];
             }
         }
-        if (lane == 0) p.counters[b] = 0;
+        const bool rep = p.poi.gt_poi != nullptr;
+        const double cr = (double)p.rec_lambda * w_eff, cp = (double)p.reproj_lambda;
+        if (lane < 9) {
+            const double Kk = rep ? (double)p.poi.K[9 * b + lane] : 0.0;
+            p.dtheta_total[9 * b + lane] = (float)((cr * s_out[1 + lane] + cp * Kk) / (double)B);
+        }
+        int last2 = 0;
+        if (lane == 0) {
+            const double Rv = rep ? (double)p.poi.Rb[b] : 0.0;
+            __stcg(p.contrib + b, cr * s_out[0] + cp * Rv);
+            last2 = (ticket_release(p.counters + B) == B - 1);
+        }
+        last2 = __shfl_sync(0xffffffffu, last2, 0);
+        if (last2) {
+            __threadfence();
+            double s = 0.0;
+            for (int i = lane; i < B; i += 32) s += __ldcg(p.contrib + i);
+            s = warp_sum(s);
+            if (lane == 0) { *p.loss_out = (float)(s / (double)B); p.counters[B] = 0; }
+        }
     }
 }
 
@@ -1180,6 +1188,7 @@ static int launch_persistent_fmt(const FusedParams& p, bool ft, int ctas, cudaSt
     }
     if (ft) kf<<<ctas, kPThreads, dyn, st>>>(p);
     else    kg<<<ctas, kPThreads, dyn, st>>>(p);
+    k_train_finalize<<<p.B, kThreads, 0, st>>>(p);
     return (int)cudaGetLastError();
 }
 
@@ -1189,8 +1198,8 @@ static int launch_persistent(const FusedParams& p, cudaStream_t st) {
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         return n;
     }();
-    const int total = p.ntiles * p.B;
-    const int ctas = total < sms ? total : sms;
+    const int chunks = ((p.ntiles + kPChunk - 1) / kPChunk) * p.B;
+    const int ctas = chunks < sms ? chunks : sms;
     const bool ft = p.vec4 && (p.W % kTileW == 0) && (p.H % 8 == 0) && (!p.xs || (((uintptr_t)p.xs & 15u) == 0));
     switch (p.t.fmt) {
         case SFH_TMPL_F32: return launch_persistent_fmt<SFH_TMPL_F32>(p, ft, ctas, st);
@@ -1258,7 +1267,7 @@ int64_t sfh_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     const int64_t tx = (W + kTileW - 1) / kTileW;
     const int64_t ntiles = tx * ((H + kWarps - 1) / kWarps);                      // k_fused, R = 1 upper bound
-    const int64_t nslots = tx * ((H + 8 * kPR - 1) / (8 * kPR)) * kPCons;         // k_train_persistent
+    const int64_t nslots = ((tx * ((H + 8 * kPR - 1) / (8 * kPR)) + kPChunk - 1) / kPChunk) * kPCons;   // k_train_persistent
     const int64_t n = ntiles > nslots ? ntiles : nslots;
     return align_up((int64_t)(B + 3) * 4, 256) + align_up((int64_t)B * 8, 256) + (int64_t)B * n * kNPart * 4;
 }
