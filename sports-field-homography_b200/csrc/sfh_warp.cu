@@ -59,6 +59,7 @@ struct FusedParams {
     // workspace
     int* counters;
     float* partials;
+    unsigned short* lists;   // persistent path: per 128x32 tile, 32 patch entries, edge patches first
 };
 
 // Geometry of one output pixel, everything the epilogues need.
@@ -687,12 +688,82 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Patch classification for the persistent path: one warp per 128 x 32 tile, one lane per 16 x 8
+// patch.  Writes the tile's edge-first patch list (32 x uint16 = 64 B) to the workspace; the
+// persistent kernel's producer then fills a pipeline stage with two bulk-async copies only.
+template <int FMT>
+__global__ void __launch_bounds__(kThreads) k_classify(const __grid_constant__ FusedParams p) {
+    const int H = p.H, W = p.W;
+    const int lane = threadIdx.x & 31;
+    const int tiles_x = (W + kTileW - 1) / kTileW;
+    const int tiles_per_sample = tiles_x * ((H + 8 * kPR - 1) / (8 * kPR));
+    const int tile = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (tile >= tiles_per_sample * p.B) return;
+    const int b = tile / tiles_per_sample, rem = tile - b * tiles_per_sample;
+    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    const int band0 = ty * (8 * kPR);
+    const int nitems = min(kPR, (H - band0 + 7) >> 3) * kWarps;
+    const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
+    int cls = -1;
+    if ((FMT != SFH_TMPL_F32) && p.t.sat != nullptr && lane < nitems) {
+        Homog Hm;
+        Hm.load(p.theta + 9 * b);
+        const int r = lane / kWarps, k = lane % kWarps;
+        float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+        bool zpos = true, zneg = true, fin = true;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int grow = min(band0 + 8 * (r + (c >> 1)), H - 1);
+            const int gcol = min(tx * kTileW + kPatchW * (k + (c & 1)), W - 1);
+            const float gu = p.xs ? __ldg(p.xs + gcol) : mesh_coord(gcol, W);
+            const float gv = p.ys ? __ldg(p.ys + grow) : mesh_coord(grow, H);
+            const Flow f = flow_at(Hm, __fmul_rn(gu, Hm.h[0]), __fmul_rn(gu, Hm.h[3]), __fmul_rn(gu, Hm.h[6]), gv);
+            const float gx = __fmul_rn(__fmaf_rn(__fadd_rn(f.x, 1.0f), Wc_f, -1.0f), 0.5f);
+            const float gy = __fmul_rn(__fmaf_rn(__fadd_rn(f.y, 1.0f), Hc_f, -1.0f), 0.5f);
+            xmin = fminf(xmin, gx); xmax = fmaxf(xmax, gx);
+            ymin = fminf(ymin, gy); ymax = fmaxf(ymax, gy);
+            fin &= (gx == gx) & (gy == gy);
+            zpos &= f.zok & (f.s > 0.f);
+            zneg &= f.zok & (f.s < 0.f);
+        }
+        fin &= (xmin > -1e9f) & (xmax < 1e9f) & (ymin > -1e9f) & (ymax < 1e9f);
+        if ((zpos | zneg) & fin) {
+            const int wmax = p.t.width + 1, hmax = p.t.height + 1;
+            const int i0 = min(max(__float2int_rd(xmin - kBoxMargin) + 1, 0), wmax);
+            const int i1 = min(max(__float2int_rd(xmax + kBoxMargin) + 2, 0), wmax);
+            const int j0 = min(max(__float2int_rd(ymin - kBoxMargin) + 1, 0), hmax);
+            const int j1 = min(max(__float2int_rd(ymax + kBoxMargin) + 2, 0), hmax);
+            const unsigned* S = p.t.sat;
+            const int sp = p.t.sat_pitch;
+            Taps<FMT> taps;
+            taps.init(p.t, 0, nullptr);
+            const unsigned ec = taps.entry_class(i0, j0);
+            const unsigned cnt = __ldg(S + (j1 + 1) * sp + (i1 + 1)) - __ldg(S + j0 * sp + (i1 + 1))
+                               - __ldg(S + (j1 + 1) * sp + i0) + __ldg(S + j0 * sp + i0);
+            if (cnt == 0u) cls = (int)ec;
+        }
+    }
+    const bool e = (lane < nitems) && cls < 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, e);
+    unsigned short* out = p.lists + (size_t)tile * kPItems;
+    if (lane < nitems) {
+        const int before = __popc(bal & ((1u << lane) - 1u)), total = __popc(bal);
+        out[e ? before : total + (lane - before)] = (unsigned short)(lane | ((cls + 1) << 8));
+    } else {
+        out[lane] = 0xffffu;
+    }
+}
+
 template <int FMT, bool FT>
 __global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(128) unsigned char s_dyn[];            // kPStages gt tiles (TMA destinations)
     __shared__ __align__(16) float s_tab[Taps<FMT>::kSmemFloats];
-    __shared__ PStage s_stage[kPStages];
-    __shared__ float s_gx[kPR + 1][kWarps + 1], s_gy[kPR + 1][kWarps + 1], s_gz[kPR + 1][kWarps + 1];   // producer scratch
+    __shared__ __align__(16) PStage s_stage[kPStages];
     __shared__ __align__(8) uint64_t s_full[kPStages], s_empty[kPStages];
 
     const int H = p.H, W = p.W;
@@ -716,10 +787,9 @@ __global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_
     }
     __syncthreads();
     taps.init(p.t, 0, s_tab);
-    const bool classify = (FMT != SFH_TMPL_F32) && (p.t.sat != nullptr);
 
     if (warp == kPCons) {
-        // =================================== producer warp ===================================
+        // ============ producer warp: two bulk-async copies per tile, nothing else ============
         int it = 0;
         int chunk = 0;
         if (lane == 0) chunk = atomicAdd(chunk_ctr, 1);
@@ -729,8 +799,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_
             if (lane == 0) next_chunk = atomicAdd(chunk_ctr, 1);        // prefetched; consumed after this chunk
             const int b = chunk / chunks_per_sample, cis = chunk - b * chunks_per_sample;
             const int t0 = cis * kPChunk, t1 = min(t0 + kPChunk, tiles_per_sample);
-            Homog Hm;
-            Hm.load(p.theta + 9 * b);
+            const float th = (lane < 9) ? __ldg(p.theta + 9 * b + lane) : 0.f;
             if (cis == 0 && p.poi.court_poi) poi_warp(p.poi, b, lane);  // the sample's court points (fp64)
             for (int rem = t0; rem < t1; ++rem, ++it) {
                 const int s = it % kPStages;
@@ -738,66 +807,17 @@ __global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_
                 PStage& st = s_stage[s];
                 const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
                 const int band0 = ty * (8 * kPR);
-                const int nitems = min(kPR, (H - band0 + 7) >> 3) * kWarps;
                 if (lane == 0) {
-                    mbar_expect_tx_only(&s_full[s], (uint32_t)kPTileBytes);
+                    mbar_expect_tx_only(&s_full[s], (uint32_t)(kPTileBytes + kPItems * 2));
                     tma_load_3d(s_dyn + (size_t)s * kPTileBytes, &p.gt_map, tx * kTileW, band0, b, &s_full[s]);
-                }
-                int cls = -1;
-                if (classify) {
-                    for (int g = lane; g < (kWarps + 1) * (kPR + 1); g += 32) {
-                        const int r = g / (kWarps + 1), k = g - r * (kWarps + 1);
-                        const int grow = min(band0 + 8 * r, H - 1), gcol = min(tx * kTileW + kPatchW * k, W - 1);
-                        const float gu = p.xs ? __ldg(p.xs + gcol) : mesh_coord(gcol, W);
-                        const float gv = p.ys ? __ldg(p.ys + grow) : mesh_coord(grow, H);
-                        const Flow f = flow_at(Hm, __fmul_rn(gu, Hm.h[0]), __fmul_rn(gu, Hm.h[3]), __fmul_rn(gu, Hm.h[6]), gv);
-                        s_gx[r][k] = __fmul_rn(__fmaf_rn(__fadd_rn(f.x, 1.0f), Wc_f, -1.0f), 0.5f);
-                        s_gy[r][k] = __fmul_rn(__fmaf_rn(__fadd_rn(f.y, 1.0f), Hc_f, -1.0f), 0.5f);
-                        s_gz[r][k] = f.zok ? __fdividef(1.0f, f.s) : __int_as_float(0x7fc00000);
-                    }
-                    __syncwarp();
-                    if (lane < nitems) {
-                        const int r = lane / kWarps, k = lane % kWarps;
-                        const float x00 = s_gx[r][k], x01 = s_gx[r][k + 1], x10 = s_gx[r + 1][k], x11 = s_gx[r + 1][k + 1];
-                        const float y00 = s_gy[r][k], y01 = s_gy[r][k + 1], y10 = s_gy[r + 1][k], y11 = s_gy[r + 1][k + 1];
-                        const float z00 = s_gz[r][k], z01 = s_gz[r][k + 1], z10 = s_gz[r + 1][k], z11 = s_gz[r + 1][k + 1];
-                        const float xmin = fminf(fminf(x00, x01), fminf(x10, x11)), xmax = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11));
-                        const float ymin = fminf(fminf(y00, y01), fminf(y10, y11)), ymax = fmaxf(fmaxf(y00, y01), fmaxf(y10, y11));
-                        const bool zpos = (z00 > 0.f) & (z01 > 0.f) & (z10 > 0.f) & (z11 > 0.f);
-                        const bool zneg = (z00 < 0.f) & (z01 < 0.f) & (z10 < 0.f) & (z11 < 0.f);
-                        const bool fin = (x00 == x00) & (x01 == x01) & (x10 == x10) & (x11 == x11) &
-                                         (y00 == y00) & (y01 == y01) & (y10 == y10) & (y11 == y11) &
-                                         (xmin > -1e9f) & (xmax < 1e9f) & (ymin > -1e9f) & (ymax < 1e9f);
-                        if ((zpos | zneg) & fin) {
-                            const int wmax = p.t.width + 1, hmax = p.t.height + 1;
-                            const int i0 = min(max(__float2int_rd(xmin - kBoxMargin) + 1, 0), wmax);
-                            const int i1 = min(max(__float2int_rd(xmax + kBoxMargin) + 2, 0), wmax);
-                            const int j0 = min(max(__float2int_rd(ymin - kBoxMargin) + 1, 0), hmax);
-                            const int j1 = min(max(__float2int_rd(ymax + kBoxMargin) + 2, 0), hmax);
-                            const unsigned* S = p.t.sat;
-                            const int sp = p.t.sat_pitch;
-                            const unsigned ec = taps.entry_class(i0, j0);
-                            const unsigned cnt = __ldg(S + (j1 + 1) * sp + (i1 + 1)) - __ldg(S + j0 * sp + (i1 + 1))
-                                               - __ldg(S + (j1 + 1) * sp + i0) + __ldg(S + j0 * sp + i0);
-                            if (cnt == 0u) cls = (int)ec;
-                        }
-                    }
-                    __syncwarp();                                       // scratch is reused by the next tile
-                }
-                // edge-first patch list: one ballot gives every rank
-                const bool e = (lane < nitems) && cls < 0;
-                const unsigned bal = __ballot_sync(0xffffffffu, e);
-                if (lane < nitems) {
-                    const int before = __popc(bal & ((1u << lane) - 1u)), total = __popc(bal);
-                    st.items[e ? before : total + (lane - before)] = (unsigned short)(lane | ((cls + 1) << 8));
-                }
-                if (lane < 9) st.theta[lane] = Hm.h[0] * 0.f + __ldg(p.theta + 9 * b + lane);
-                if (lane == 0) {
-                    st.b = b; st.tx = tx; st.ty = ty; st.nitems = nitems;
+                    bulk_load(st.items, p.lists + ((size_t)b * tiles_per_sample + rem) * kPItems, kPItems * 2, &s_full[s]);
+                    st.b = b; st.tx = tx; st.ty = ty;
+                    st.nitems = min(kPR, (H - band0 + 7) >> 3) * kWarps;
                     st.slot = (rem == t1 - 1) ? (b * chunks_per_sample + cis) : -1;
                 }
+                if (lane < 9) st.theta[lane] = th;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&s_full[s]);                 // + the TMA's tx bytes => phase completes
+                if (lane == 0) mbar_arrive(&s_full[s]);                 // + the copies' tx bytes => phase completes
             }
             chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
         }
@@ -1139,6 +1159,11 @@ static int setup_ws(FusedParams& p, void* ws, int64_t ws_bytes) {
     p.counters = (int*)ws;                                             // [B+3]: samples, batch, tile ticket, done
     p.contrib = (double*)((char*)ws + align_up((int64_t)(p.B + 3) * 4, 256));   // [B]
     p.partials = (float*)((char*)p.contrib + align_up((int64_t)p.B * 8, 256));
+    const int64_t tx = (p.W + kTileW - 1) / kTileW;
+    const int64_t ntiles = tx * ((p.H + kWarps - 1) / kWarps);
+    const int64_t nslots = ((tx * ((p.H + 8 * kPR - 1) / (8 * kPR)) + kPChunk - 1) / kPChunk) * kPCons;
+    const int64_t n = ntiles > nslots ? ntiles : nslots;
+    p.lists = (unsigned short*)((char*)p.partials + align_up((int64_t)p.B * n * kNPart * 4, 256));
     return 0;
 }
 
@@ -1186,6 +1211,8 @@ static int launch_persistent_fmt(const FusedParams& p, bool ft, int ctas, cudaSt
         cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         raised = true;
     }
+    const int total_tiles = p.ntiles * p.B;
+    k_classify<FMT><<<(total_tiles + kWarps - 1) / kWarps, kThreads, 0, st>>>(p);
     if (ft) kf<<<ctas, kPThreads, dyn, st>>>(p);
     else    kg<<<ctas, kPThreads, dyn, st>>>(p);
     k_train_finalize<<<p.B, kThreads, 0, st>>>(p);
@@ -1269,7 +1296,9 @@ int64_t sfh_workspace_bytes(int B, int H, int W) {
     const int64_t ntiles = tx * ((H + kWarps - 1) / kWarps);                      // k_fused, R = 1 upper bound
     const int64_t nslots = ((tx * ((H + 8 * kPR - 1) / (8 * kPR)) + kPChunk - 1) / kPChunk) * kPCons;   // k_train_persistent
     const int64_t n = ntiles > nslots ? ntiles : nslots;
-    return align_up((int64_t)(B + 3) * 4, 256) + align_up((int64_t)B * 8, 256) + (int64_t)B * n * kNPart * 4;
+    const int64_t lists = (int64_t)B * tx * ((H + 8 * kPR - 1) / (8 * kPR)) * kPItems * 2;   // patch lists, 64 B per tile
+    return align_up((int64_t)(B + 3) * 4, 256) + align_up((int64_t)B * 8, 256) +
+           align_up((int64_t)B * n * kNPart * 4, 256) + lists;
 }
 
 int sfh_template_pack(const float* tmpl, int Hc, int Wc, const float* palette_host, int n_palette,
