@@ -675,7 +675,7 @@ constexpr int kPItems = kPR * kWarps;            // 32 patches per tile
 constexpr int kPTileBytes = kPR * 8 * kTileW * 8;
 constexpr int kPChunk = 6;                       // tiles per chunk (consecutive tiles of one sample)
 
-struct PStage {
+struct __align__(16) PStage {
     unsigned short items[kPItems];
     float theta[9];
     int b, tx, ty, nitems, slot;                 // nitems < 0: no more tiles; slot >= 0: last tile of its chunk
