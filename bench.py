@@ -255,18 +255,33 @@ def time_workload(wl, steps, warmup, use_graph, dist_vec=None):
     import torch.distributed as dist
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
+    pending = []
+
     def one(i):
         r = wl.step(i)
         if multi and isinstance(r, dict) and "loss" in r:
-            dist_vec[0].copy_(r["loss"])       # local mean loss (equal shard sizes); [1] carries the count
-            dist.all_reduce(dist_vec)          # global loss numerator + frame count
+            slot = dist_vec[i % dist_vec.shape[0]]
+            slot[0].copy_(r["loss"])           # local mean loss (equal shard sizes); [1] carries the frame count
+            # global loss numerator + frame count.  Nothing on the next step depends on it,
+            # so the all-reduce runs beside the next step's kernel and is joined once per buffer rotation.
+            pending.append(dist.all_reduce(slot, async_op=True))
+            if len(pending) >= wl.nsets:
+                for w in pending:
+                    w.wait()
+                pending.clear()
         return r
+
+    def drain():
+        for w in pending:
+            w.wait()
+        pending.clear()
 
     graphs = None
     mode = "eager"
     with torch.no_grad():
         for i in range(max(warmup, wl.nsets)):
             one(i)
+        drain()
         torch.cuda.synchronize()
         if use_graph and wl.kind != "fwd":
             try:
@@ -274,17 +289,18 @@ def time_workload(wl, steps, warmup, use_graph, dist_vec=None):
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
-                    for i in range(wl.nsets):
-                        g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g, stream=side):
+                    g = torch.cuda.CUDAGraph()      # ONE graph = one rotation through the buffer sets
+                    with torch.cuda.graph(g, stream=side):
+                        for i in range(wl.nsets):
                             one(i)
-                        graphs.append(g)
+                        drain()
+                    graphs.append(g)
                 torch.cuda.current_stream().wait_stream(side)
                 torch.cuda.synchronize()
                 for g in graphs:
                     g.replay()
                 torch.cuda.synchronize()
-                mode = "cuda_graph"
+                mode = f"cuda_graph ({wl.nsets} steps per graph)"
             except Exception as e:      # capture unsupported in this configuration: time eagerly
                 sys.stderr.write(f"[bench] graph capture failed ({e!r}); timing eager launches\n")
                 graphs = None
@@ -295,11 +311,15 @@ def time_workload(wl, steps, warmup, use_graph, dist_vec=None):
         t0 = time.perf_counter()
         e0.record()
         if graphs:
-            for i in range(steps):
-                graphs[i % wl.nsets].replay()
+            for _ in range(steps // wl.nsets):
+                graphs[0].replay()
+            for i in range(steps % wl.nsets):   # remainder so that EXACTLY `steps` steps are timed
+                one(i)
+            drain()
         else:
             for i in range(steps):
                 one(i)
+            drain()
         e1.record()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
@@ -382,7 +402,7 @@ def main_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-        dist_vec = torch.zeros(2, dtype=torch.float64, device=dev)
+        dist_vec = torch.zeros(8, 2, dtype=torch.float64, device=dev)
         dist.all_reduce(dist_vec)
 
     sfh_b200._lib.lib()                        # fail loudly if the CUDA library is missing

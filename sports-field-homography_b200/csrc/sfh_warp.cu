@@ -21,7 +21,8 @@
 namespace sfh {
 
 struct FusedParams {
-    alignas(64) CUtensorMap gt_map;   // TMA descriptor of gt [B,H,W] int64, box 128 x 8R x 1
+    alignas(64) CUtensorMap gt_map;   // TMA descriptor: kEpiLoss gt [B,H,W] int64, box 128 x 8R x 1;
+                                      // kEpiPredict (ratio 2, nc 4) logits [B,4,h,w] fp32, box 64 x 4R x 4 x 1
     const float* theta;
     const float* xs;
     const float* ys;
@@ -30,7 +31,7 @@ struct FusedParams {
     int rows_per_warp;   // R: a CTA covers 128 x 8R output pixels = 8R patches of 16 x 8
     int ntiles;          // CTAs per sample
     int vec4;            // W % 4 == 0 and all row bases 16-byte aligned
-    int use_tma;         // kEpiLoss: the CTA's gt tile is staged in shared memory by one TMA load
+    int use_tma;         // the CTA's gt tile (loss) / logits tile (predict) is staged in smem by one TMA load
     // kEpiStore / kEpiBwd
     float* out_f;        // [B,C,H,W]
     const float* grad_out;
@@ -128,15 +129,20 @@ struct GradAcc {
     }
 };
 
+// Cross entropy of one pixel with 4 logits in registers: lse(l) - l[cls].  exp/log go through the
+// MUFU ex2/lg2 units (rel. error ~1e-6 on terms <= 1, i.e. ~1e-6 absolute on a score of O(1);
+// tests hold the per-sample mean to 1e-5 relative against torch's log_softmax).
+__device__ __forceinline__ float ce4(float l0, float l1, float l2, float l3, int cls) {
+    const float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
+    const float k = 1.4426950408889634f;
+    const float se = exp2f((l0 - mx) * k) + exp2f((l1 - mx) * k) + exp2f((l2 - mx) * k) + exp2f((l3 - mx) * k);
+    const float sel = cls == 0 ? l0 : cls == 1 ? l1 : cls == 2 ? l2 : l3;
+    return fmaf(__log2f(se), 0.6931471805599453f, mx) - sel;
+}
+
 // log-sum-exp cross entropy of one pixel, nc logits strided by `cs` (F.cross_entropy, reduction none).
 __device__ __forceinline__ float ce_pixel(const float* lg, size_t cs, int nc, int cls) {
-    if (nc == 4) {
-        const float l0 = __ldcs(lg), l1 = __ldcs(lg + cs), l2 = __ldcs(lg + 2 * cs), l3 = __ldcs(lg + 3 * cs);
-        const float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
-        const float se = expf(l0 - mx) + expf(l1 - mx) + expf(l2 - mx) + expf(l3 - mx);
-        const float sel = cls == 0 ? l0 : cls == 1 ? l1 : cls == 2 ? l2 : l3;
-        return (logf(se) + mx) - sel;
-    }
+    if (nc == 4) return ce4(__ldcs(lg), __ldcs(lg + cs), __ldcs(lg + 2 * cs), __ldcs(lg + 3 * cs), cls);
     float mx = -INFINITY, sel = 0.f;
     for (int c = 0; c < nc; ++c) {
         const float v = __ldg(lg + c * cs);
@@ -188,6 +194,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int x, int y, int z, int w, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(w), "r"(smem_u32(bar)) : "memory");
 }
 
 // Reduce 16 per-lane values across the warp with 16 shuffles: after the butterfly, lane L holds
@@ -260,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     const int band0 = ty * (8 * R);                       // first row of the CTA tile
     const int nitems = min(R, (H - band0 + 7) >> 3) * kWarps;   // patches with at least one row inside the image
     const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
-    const bool tma = (EPI == kEpiLoss) && p.use_tma;
+    const bool tma = (EPI == kEpiLoss || EPI == kEpiPredict) && p.use_tma;
 
     if (tma && threadIdx.x == 0) mbar_init(&s_bar, 1);
     Taps<FMT> taps;
@@ -284,8 +296,13 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     }
     __syncthreads();                         // s_bar initialised, tables and corner grid written
     if (tma && threadIdx.x == 0) {
-        mbar_expect_tx(&s_bar, (uint32_t)(R * 8 * kTileW * sizeof(long long)));
-        tma_load_3d(s_dyn, &p.gt_map, tx * kTileW, band0, b, &s_bar);
+        if (EPI == kEpiLoss) {
+            mbar_expect_tx(&s_bar, (uint32_t)(R * 8 * kTileW * sizeof(long long)));
+            tma_load_3d(s_dyn, &p.gt_map, tx * kTileW, band0, b, &s_bar);
+        } else {                             // logits [B,4,h,w]: 64 x 4R x 4 floats under this 128 x 8R tile
+            mbar_expect_tx(&s_bar, (uint32_t)(R * 4 * (kTileW / 2) * 4 * sizeof(float)));
+            tma_load_4d(s_dyn, &p.gt_map, tx * (kTileW / 2), band0 >> 1, 0, b, &s_bar);
+        }
     }
     taps.init(p.t, b, s_tab);
     int cls = -1;
@@ -412,10 +429,19 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                     for (int j = 0; j < 4; ++j)
                         if (FT || col + j < W) score_sum += ce_pixel(lg + j, cs, p.nc, ci);
                 } else if (p.score && p.ratio == 2 && row_ok && !(row & 1)) {
-                    const size_t cs = (size_t)p.lh * p.lw;
-                    const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)(row >> 1) * p.lw + (col >> 1);
-                    if (FT || col < W) score_sum += ce_pixel(lg, cs, p.nc, ci);
-                    if (FT || col + 2 < W) score_sum += ce_pixel(lg + 1, cs, p.nc, ci);
+                    if (tma) {
+                        const float* sl = reinterpret_cast<const float*>(s_dyn) + (pr * 4 + (ly >> 1)) * (kTileW / 2) + pk * 8 + lx * 2;
+                        const int cst = R * 4 * (kTileW / 2);
+                        const float2 a0 = *reinterpret_cast<const float2*>(sl), a1 = *reinterpret_cast<const float2*>(sl + cst);
+                        const float2 a2 = *reinterpret_cast<const float2*>(sl + 2 * cst), a3 = *reinterpret_cast<const float2*>(sl + 3 * cst);
+                        if (FT || col < W) score_sum += ce4(a0.x, a1.x, a2.x, a3.x, ci);
+                        if (FT || col + 2 < W) score_sum += ce4(a0.y, a1.y, a2.y, a3.y, ci);
+                    } else {
+                        const size_t cs = (size_t)p.lh * p.lw;
+                        const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)(row >> 1) * p.lw + (col >> 1);
+                        if (FT || col < W) score_sum += ce_pixel(lg, cs, p.nc, ci);
+                        if (FT || col + 2 < W) score_sum += ce_pixel(lg + 1, cs, p.nc, ci);
+                    }
                 }
             }
             continue;                        // kEpiBwd: zero gradient, grad_out is not even read
@@ -547,10 +573,19 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                     if (FT || col + j < W) score_sum += ce_pixel(lg + j, cs, p.nc, ci[j]);
             } else if (p.score && p.ratio == 2 && row_ok && !(row & 1)) {
                 // F.interpolate(nearest) to (H/2, W/2) picks source pixel (2i, 2j)
-                const size_t cs = (size_t)p.lh * p.lw;
-                const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)(row >> 1) * p.lw + (col >> 1);
-                if (FT || col < W) score_sum += ce_pixel(lg, cs, p.nc, ci[0]);
-                if (FT || col + 2 < W) score_sum += ce_pixel(lg + 1, cs, p.nc, ci[2]);
+                if (tma) {
+                    const float* sl = reinterpret_cast<const float*>(s_dyn) + (pr * 4 + (ly >> 1)) * (kTileW / 2) + pk * 8 + lx * 2;
+                    const int cst = R * 4 * (kTileW / 2);
+                    const float2 a0 = *reinterpret_cast<const float2*>(sl), a1 = *reinterpret_cast<const float2*>(sl + cst);
+                    const float2 a2 = *reinterpret_cast<const float2*>(sl + 2 * cst), a3 = *reinterpret_cast<const float2*>(sl + 3 * cst);
+                    if (FT || col < W) score_sum += ce4(a0.x, a1.x, a2.x, a3.x, ci[0]);
+                    if (FT || col + 2 < W) score_sum += ce4(a0.y, a1.y, a2.y, a3.y, ci[2]);
+                } else {
+                    const size_t cs = (size_t)p.lh * p.lw;
+                    const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)(row >> 1) * p.lw + (col >> 1);
+                    if (FT || col < W) score_sum += ce_pixel(lg, cs, p.nc, ci[0]);
+                    if (FT || col + 2 < W) score_sum += ce_pixel(lg + 1, cs, p.nc, ci[2]);
+                }
             }
         }
     }
@@ -1191,7 +1226,9 @@ static int launch_fused(const FusedParams& p, cudaStream_t st) {
     dim3 grid(tiles_x, p.ntiles / tiles_x, p.B);
     const bool ft = p.vec4 && (p.W % kTileW == 0) && (p.H % 8 == 0) &&
                     (!p.xs || (((uintptr_t)p.xs & 15u) == 0));
-    const size_t dyn = (EPI == kEpiLoss && p.use_tma) ? (size_t)p.rows_per_warp * 8 * kTileW * sizeof(long long) : 0;
+    const size_t dyn = !p.use_tma ? 0
+                     : (EPI == kEpiLoss) ? (size_t)p.rows_per_warp * 8 * kTileW * sizeof(long long)
+                     : (EPI == kEpiPredict) ? (size_t)p.rows_per_warp * 4 * (kTileW / 2) * 4 * sizeof(float) : 0;
     switch (p.t.fmt) {
         case SFH_TMPL_F32: return launch_fmt<SFH_TMPL_F32, MODE, EPI>(p, grid, dyn, ft, st);
         case SFH_TMPL_Q2:  return launch_fmt<SFH_TMPL_Q2, MODE, EPI>(p, grid, dyn, ft, st);
@@ -1262,6 +1299,20 @@ static bool make_gt_map(FusedParams& p) {
     const cuuint32_t box[3] = {(cuuint32_t)kTileW, (cuuint32_t)(8 * p.rows_per_warp), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(&p.gt_map, CU_TENSOR_MAP_DATA_TYPE_INT64, 3, (void*)p.gt, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// logits [B,4,h,w] fp32 (h = H/2, w = W/2) -> 4-D tensor map, box 64 x 4R x 4 x 1
+static bool make_logits_map(FusedParams& p) {
+    static const bool off = getenv("SFH_NO_TMA") != nullptr;
+    EncodeTiledFn enc = encode_tiled();
+    if (off || !enc || !aligned16(p.logits) || p.nc != 4 || p.ratio != 2 || p.rows_per_warp > 16 || (p.lw % 4) != 0) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)p.lw, (cuuint64_t)p.lh, 4, (cuuint64_t)p.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.lw * 4, (cuuint64_t)p.lw * p.lh * 4, (cuuint64_t)p.lw * p.lh * 16};
+    const cuuint32_t box[4] = {(cuuint32_t)(kTileW / 2), (cuuint32_t)(4 * p.rows_per_warp), 4, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(&p.gt_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.logits, dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -1417,6 +1468,7 @@ int sfh_predict_tail(const sfh_template* tmpl, const sfh_predict_tail_args* a, v
         if ((rc = setup_ws(p, a->workspace, a->workspace_bytes))) return rc;
         p.logits = a->logits; p.lh = a->h; p.lw = a->w; p.score = a->score;
         p.ratio = (a->h == a->H && a->w == a->W) ? 1 : (2 * a->h == a->H && 2 * a->w == a->W) ? 2 : 0;
+        p.use_tma = make_logits_map(p) ? 1 : 0;
     }
     const bool poi_tail = a->court_poi != nullptr;
     if (poi_tail) {
