@@ -364,8 +364,40 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 
     if (tma) mbar_wait(&s_bar, 0);           // gt tile has landed (it streamed in behind the prologue)
 
+    // ---- static, deterministic, cost-balanced schedule -------------------------------------
+    // list = [E edge patches][U edge-free patches].  Warp w takes edge entries w, w+8, ... and a
+    // contiguous run of edge-free entries sized so that  kEdgeCost*edges + edge_free  is equal
+    // across warps (an edge patch costs ~10x an edge-free one); a function of (E, U) only.
+    int nedge = 0;
+#pragma unroll
+    for (int w = 0; w < kMaxR * kWarps / 32; ++w) nedge += s_ecnt[w];
+    const int nuni = nitems - nedge;
+    int u_begin = 0, u_end = 0;
+    {
+        constexpr int kEdgeCost = (EPI == kEpiLoss) ? 10 : (EPI == kEpiBwd) ? 12 : 6;
+        const int t8 = kEdgeCost * nedge + nuni;             // 8 x the ideal cost per warp
+        int want[kWarps], tot = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const int ce = (nedge - w + kWarps - 1) / kWarps;
+            want[w] = max(0, t8 - kWarps * kEdgeCost * ce);
+            tot += want[w];
+        }
+        int pre = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const int lo = tot > 0 ? (int)(((long long)nuni * pre) / tot) : (nuni * w) / kWarps;
+            pre += want[w];
+            const int hi = tot > 0 ? (int)(((long long)nuni * pre) / tot) : (nuni * (w + 1)) / kWarps;
+            if (w == warp) { u_begin = lo; u_end = hi; }
+        }
+    }
+    const int my_edges = (nedge - warp + kWarps - 1) / kWarps;
+    const int my_items = my_edges + (u_end - u_begin);
+
 #pragma unroll 1
-    for (int it = warp; it < nitems; it += kWarps) {
+    for (int n = 0; n < my_items; ++n) {
+        const int it = (n < my_edges) ? warp + n * kWarps : nedge + u_begin + (n - my_edges);
         const unsigned item = s_items[it];
         const int pr = (item & 0xffu) >> 3, pk = item & 7u, pc = (int)(item >> 8) - 1;
         const int row = band0 + pr * 8 + ly;
@@ -1206,7 +1238,7 @@ template <int FMT, int MODE, int EPI>
 static int launch_fmt(const FusedParams& p, dim3 grid, size_t dyn, bool ft, cudaStream_t st) {
     auto kf = k_fused<FMT, MODE, EPI, true>;
     auto kg = k_fused<FMT, MODE, EPI, false>;
-    if (dyn > 48 * 1024) {
+    if (dyn > 32 * 1024) {                     // static (~9 KiB) + dynamic above 48 KiB needs the opt-in
         static bool raised = false;            // per instantiation; idempotent, so a race is harmless
         if (!raised) {
             cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8 * kTileW * 8);
