@@ -372,25 +372,22 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 #pragma unroll
     for (int w = 0; w < kMaxR * kWarps / 32; ++w) nedge += s_ecnt[w];
     const int nuni = nitems - nedge;
-    int u_begin = 0, u_end = 0;
+    int u_begin, u_end;
     {
         constexpr int kEdgeCost = (EPI == kEpiLoss) ? 10 : (EPI == kEpiBwd) ? 12 : 6;
         const int t8 = kEdgeCost * nedge + nuni;             // 8 x the ideal cost per warp
-        int want[kWarps], tot = 0;
+        int pre = 0, tot = 0;                                // lane l < 8 evaluates warp l's share
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
-            const int ce = (nedge - w + kWarps - 1) / kWarps;
-            want[w] = max(0, t8 - kWarps * kEdgeCost * ce);
-            tot += want[w];
+            const int want = max(0, t8 - kWarps * kEdgeCost * ((nedge - w + kWarps - 1) >> 3));
+            if (w < (lane & 7)) pre += want;
+            tot += want;
         }
-        int pre = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const int lo = tot > 0 ? (int)(((long long)nuni * pre) / tot) : (nuni * w) / kWarps;
-            pre += want[w];
-            const int hi = tot > 0 ? (int)(((long long)nuni * pre) / tot) : (nuni * (w + 1)) / kWarps;
-            if (w == warp) { u_begin = lo; u_end = hi; }
-        }
+        const int mine = max(0, t8 - kWarps * kEdgeCost * ((nedge - (lane & 7) + kWarps - 1) >> 3));
+        const int lo = tot > 0 ? (nuni * pre) / tot : (nuni * (lane & 7)) >> 3;
+        const int hi = tot > 0 ? (nuni * (pre + mine)) / tot : (nuni * ((lane & 7) + 1)) >> 3;
+        u_begin = __shfl_sync(0xffffffffu, lo, warp);
+        u_end = __shfl_sync(0xffffffffu, hi, warp);
     }
     const int my_edges = (nedge - warp + kWarps - 1) / kWarps;
     const int my_items = my_edges + (u_end - u_begin);
