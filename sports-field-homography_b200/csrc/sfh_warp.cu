@@ -31,7 +31,6 @@ struct FusedParams {
     int rows_per_warp;   // R: a CTA covers 128 x 8R output pixels = 8R patches of 16 x 8
     int ntiles;          // CTAs per sample
     int vec4;            // W % 4 == 0 and all row bases 16-byte aligned
-    int edge_cost;       // schedule weight of an edge patch relative to an edge-free one
     int use_tma;         // the CTA's gt tile (loss) / logits tile (predict) is staged in smem by one TMA load
     // kEpiStore / kEpiBwd
     float* out_f;        // [B,C,H,W]
@@ -365,30 +364,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 
     if (tma) mbar_wait(&s_bar, 0);           // gt tile has landed (it streamed in behind the prologue)
 
-    // ---- static, deterministic, cost-balanced schedule -------------------------------------
-    // list = [E edge patches][U edge-free patches], dealt to the 8 warps round-robin so that at any
-    // time the warps work on neighbouring patches (their 64 B row segments complete 512 B of a row
-    // together).  An edge patch costs ~edge_cost edge-free ones, so the warps that got one edge
-    // patch fewer (w >= E % 8) first share `edge_cost` extra rounds of edge-free patches among
-    // themselves; the rest is dealt to all 8.  The schedule is a function of (E, U) only.
-    int nedge = 0;
-#pragma unroll
-    for (int w = 0; w < kMaxR * kWarps / 32; ++w) nedge += s_ecnt[w];
-    const int nuni = nitems - nedge;
-    const int rem = nedge & (kWarps - 1);
-    const int n_light = rem ? kWarps - rem : 0;
-    const int extra = min(nuni, p.edge_cost * n_light);
-    const int my_edges = (nedge - warp + kWarps - 1) / kWarps;
-    const int my_extra = (n_light && warp >= rem) ? (extra - (warp - rem) + n_light - 1) / n_light : 0;
-    const int my_rest = (nuni - extra - warp + kWarps - 1) / kWarps;      // may be <= 0
-    const int my_items = my_edges + my_extra + max(my_rest, 0);
-
 #pragma unroll 1
-    for (int n = 0; n < my_items; ++n) {
-        int it;
-        if (n < my_edges) it = warp + n * kWarps;
-        else if (n < my_edges + my_extra) it = nedge + (warp - rem) + (n - my_edges) * n_light;
-        else it = nedge + extra + warp + (n - my_edges - my_extra) * kWarps;
+    for (int it = warp; it < nitems; it += kWarps) {
         const unsigned item = s_items[it];
         const int pr = (item & 0xffu) >> 3, pk = item & 7u, pc = (int)(item >> 8) - 1;
         const int row = band0 + pr * 8 + ly;
@@ -1207,8 +1184,6 @@ static void fill_common(FusedParams& p, const float* theta, const sfh_template* 
         while (R > 1 && (int64_t)tiles_x * ((H + kWarps * R - 1) / (kWarps * R)) * B < 4 * 3 * 148) R >>= 1;
     p.rows_per_warp = R;
     p.ntiles = tiles_x * ((H + kWarps * R - 1) / (kWarps * R));
-    static const int ec = [] { const char* e = getenv("SFH_EDGE_COST"); return e ? atoi(e) : 4; }();
-    p.edge_cost = ec;
 }
 
 static inline bool aligned16(const void* q) { return ((uintptr_t)q & 15u) == 0; }
