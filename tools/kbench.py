@@ -19,6 +19,8 @@ ap.add_argument("--only", default="")
 ap.add_argument("--n", type=int, default=30)
 ap.add_argument("--sets", type=int, default=4)
 ap.add_argument("--hd", action="store_true")
+ap.add_argument("--oob", action="store_true", help="push every sample fully out of bounds: all patches edge-free")
+ap.add_argument("--exact", action="store_true", help="disable the edge-free patch shortcut")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 PEAK = 6545.3
@@ -45,11 +47,13 @@ def run(tag, fn, nbytes):
 cfgs = [(640, 360, 64)] + ([(1280, 720, 32)] if a.hd else [])
 for (W, H, B) in cfgs:
     tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (W, H), 4, 1)
-    stb = sfh_b200.STNWarpStage(tmpl.to(dev), poi.to(dev), (W, H), 4)
+    stb = sfh_b200.STNWarpStage(tmpl.to(dev), poi.to(dev), (W, H), 4, exact=a.exact)
     stn = sfh_b200.STNWarpStage(tmpl.to(dev), poi.to(dev), (W, H), 4, warp_with_nearest=True)
     sets = []
     for i in range(a.sets):
         th = synth.theta_family_a(B, 50 + i).to(dev)
+        if a.oob:
+            th[:, 0, 0, 2] = 5.0
         gt = stn.predict_tail(synth.perturb(th.cpu(), seed=i).to(dev), None, False, False)["warp_mask"].to(torch.int64)
         gt_poi = stb.transform_poi(synth.perturb(th.cpu(), seed=9).to(dev)).detach()
         nz = torch.ones(B, poi.shape[1], device=dev)
