@@ -42,6 +42,10 @@ extern "C" {
 #define SFH_LOSS_MSE      0
 #define SFH_LOSS_SMOOTHL1 1
 
+/* dtype of the ground-truth masks handed to sfh_warp_loss_fwd_bwd */
+#define SFH_GT_I64 0   /* int64, what the reference's dataset yields (utils/dataset.py:167) */
+#define SFH_GT_U8  1   /* uint8 class ids: the narrow surface of SURVEY.md §8 f-1 (8x less PCIe / HBM traffic) */
+
 /* template storage formats */
 #define SFH_TMPL_F32 0  /* [Bt,C,Hc,Wc] fp32 as open_court_template returns it (utils/dataset.py:47-61) */
 #define SFH_TMPL_Q2  1  /* quad-packed palette indices, 2 bits/tap, uint8  [(Hc+2) x pitch] */
@@ -116,7 +120,7 @@ typedef struct sfh_train_tail_args {
     const float*   theta;            /* [B,3,3] */
     const float*   xs;               /* [W] nullable */
     const float*   ys;               /* [H] nullable */
-    const int64_t* gt;               /* [B,H,W] int64 class ids (utils/dataset.py:167) */
+    const void*    gt;               /* [B,H,W] class ids, int64 (utils/dataset.py:167) or uint8, see gt_dtype */
     int32_t B, H, W;
     int32_t nc;                      /* mask_classes */
     int32_t kind;                    /* SFH_LOSS_* */
@@ -135,6 +139,7 @@ typedef struct sfh_train_tail_args {
     const void* weights;             /* [B] fp32/fp64, nullable (w = 1) */
     int32_t weights_f64;
     int32_t weights_outer;
+    int32_t gt_dtype;                /* SFH_GT_I64 (default 0) | SFH_GT_U8 */
     float   rec_lambda;
     float   reproj_lambda;
     float*  loss_out;                /* scalar, nullable */

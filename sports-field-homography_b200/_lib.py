@@ -41,7 +41,7 @@ class SfhTrainTailArgs(C.Structure):
                 ("gt_poi", C.c_void_p), ("nonzeros", C.c_void_p), ("num_nonzero", C.c_void_p),
                 ("poi_out", C.c_void_p), ("R_b", C.c_void_p), ("dRb_dtheta", C.c_void_p),
                 ("weights", C.c_void_p), ("weights_f64", C.c_int32), ("weights_outer", C.c_int32),
-                ("rec_lambda", C.c_float), ("reproj_lambda", C.c_float),
+                ("gt_dtype", C.c_int32), ("rec_lambda", C.c_float), ("reproj_lambda", C.c_float),
                 ("loss_out", C.c_void_p), ("dtheta_total", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 

@@ -37,7 +37,8 @@ struct FusedParams {
     const float* grad_out;
     float* dtheta;       // [B,9]
     // kEpiLoss
-    const long long* gt;
+    const long long* gt;     // int64 class ids (reference dtype) ...
+    const unsigned char* gt8; // ... or uint8 class ids (narrow surface); exactly one is set
     int nc, kind, nc_pow2;
     float inv_nc, invN;
     float* Lb;
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     __syncthreads();                         // s_bar initialised, tables and corner grid written
     if (tma && threadIdx.x == 0) {
         if (EPI == kEpiLoss) {
-            mbar_expect_tx(&s_bar, (uint32_t)(R * 8 * kTileW * sizeof(long long)));
+            mbar_expect_tx(&s_bar, (uint32_t)(R * 8 * kTileW * (p.gt8 ? 1 : sizeof(long long))));
             tma_load_3d(s_dyn, &p.gt_map, tx * kTileW, band0, b, &s_bar);
         } else {                             // logits [B,4,h,w]: 64 x 4R x 4 floats under this 128 x 8R tile
             mbar_expect_tx(&s_bar, (uint32_t)(R * 4 * (kTileW / 2) * 4 * sizeof(float)));
@@ -378,14 +379,26 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 
         float tgt[4];
         if (EPI == kEpiLoss) {
-            Gt4 g;
-            if (tma) {                       // zero-filled outside the image by the TMA unit
-                const longlong2* sp2 = reinterpret_cast<const longlong2*>(s_gt + (pr * 8 + ly) * kTileW + pk * kPatchW + lx * 4);
-                g.lo = sp2[0]; g.hi = sp2[1];
+            float gf[4];
+            if (p.gt8) {
+                uchar4 g8;
+                if (tma) g8 = *reinterpret_cast<const uchar4*>(s_dyn + (pr * 8 + ly) * kTileW + pk * kPatchW + lx * 4);
+                else if (vec) g8 = __ldcs(reinterpret_cast<const uchar4*>(p.gt8 + rowbase));
+                else {
+                    g8.x = (row_ok && col + 0 < W) ? p.gt8[rowbase + 0] : 0; g8.y = (row_ok && col + 1 < W) ? p.gt8[rowbase + 1] : 0;
+                    g8.z = (row_ok && col + 2 < W) ? p.gt8[rowbase + 2] : 0; g8.w = (row_ok && col + 3 < W) ? p.gt8[rowbase + 3] : 0;
+                }
+                gf[0] = (float)g8.x; gf[1] = (float)g8.y; gf[2] = (float)g8.z; gf[3] = (float)g8.w;
             } else {
-                g = load_gt<FT>(p.gt, rowbase, col, W, vec, row_ok);
+                Gt4 g;
+                if (tma) {                   // zero-filled outside the image by the TMA unit
+                    const longlong2* sp2 = reinterpret_cast<const longlong2*>(s_gt + (pr * 8 + ly) * kTileW + pk * kPatchW + lx * 4);
+                    g.lo = sp2[0]; g.hi = sp2[1];
+                } else {
+                    g = load_gt<FT>(p.gt, rowbase, col, W, vec, row_ok);
+                }
+                gf[0] = (float)(int)g.lo.x; gf[1] = (float)(int)g.lo.y; gf[2] = (float)(int)g.hi.x; gf[3] = (float)(int)g.hi.y;
             }
-            const float gf[4] = {(float)(int)g.lo.x, (float)(int)g.lo.y, (float)(int)g.hi.x, (float)(int)g.hi.y};
 #pragma unroll
             for (int j = 0; j < 4; ++j)      // class ids: the low 32 bits carry the value
                 tgt[j] = p.nc_pow2 ? __fmul_rn(gf[j], p.inv_nc) : __fdiv_rn(gf[j], ncf);
@@ -1227,7 +1240,7 @@ static int launch_fused(const FusedParams& p, cudaStream_t st) {
     const bool ft = p.vec4 && (p.W % kTileW == 0) && (p.H % 8 == 0) &&
                     (!p.xs || (((uintptr_t)p.xs & 15u) == 0));
     const size_t dyn = !p.use_tma ? 0
-                     : (EPI == kEpiLoss) ? (size_t)p.rows_per_warp * 8 * kTileW * sizeof(long long)
+                     : (EPI == kEpiLoss) ? (size_t)p.rows_per_warp * 8 * kTileW * (p.gt8 ? 1 : sizeof(long long))
                      : (EPI == kEpiPredict) ? (size_t)p.rows_per_warp * 4 * (kTileW / 2) * 4 * sizeof(float) : 0;
     switch (p.t.fmt) {
         case SFH_TMPL_F32: return launch_fmt<SFH_TMPL_F32, MODE, EPI>(p, grid, dyn, ft, st);
@@ -1293,12 +1306,14 @@ static EncodeTiledFn encode_tiled() {
 static bool make_gt_map(FusedParams& p) {
     static const bool off = getenv("SFH_NO_TMA") != nullptr;
     EncodeTiledFn enc = encode_tiled();
-    if (off || !enc || !aligned16(p.gt) || p.rows_per_warp > 8) return false;
+    const void* base = p.gt8 ? (const void*)p.gt8 : (const void*)p.gt;
+    const cuuint64_t esz = p.gt8 ? 1 : 8;
+    if (off || !enc || !aligned16(base) || p.rows_per_warp > (p.gt8 ? 16 : 8) || ((p.W * esz) % 16) != 0) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
-    const cuuint64_t strides[2] = {(cuuint64_t)p.W * 8, (cuuint64_t)p.W * p.H * 8};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.W * esz, (cuuint64_t)p.W * p.H * esz};
     const cuuint32_t box[3] = {(cuuint32_t)kTileW, (cuuint32_t)(8 * p.rows_per_warp), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    return enc(&p.gt_map, CU_TENSOR_MAP_DATA_TYPE_INT64, 3, (void*)p.gt, dims, strides, box, estr,
+    return enc(&p.gt_map, p.gt8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_INT64, 3, (void*)base, dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -1412,15 +1427,18 @@ int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* a
     if (tmpl->channels != 1) return SFH_E_BADARG;
     if (a->kind != SFH_LOSS_MSE && a->kind != SFH_LOSS_SMOOTHL1) return SFH_E_BADMODE;
     if (a->loss_out && !a->dtheta_total) return SFH_E_BADARG;
+    if (a->gt_dtype != SFH_GT_I64 && a->gt_dtype != SFH_GT_U8) return SFH_E_BADARG;
     FusedParams p;
     fill_common(p, a->theta, tmpl, a->xs, a->ys, a->B, a->H, a->W);
     if ((rc = setup_ws(p, a->workspace, a->workspace_bytes))) return rc;
-    p.gt = (const long long*)a->gt; p.nc = a->nc; p.kind = a->kind;
+    if (a->gt_dtype == SFH_GT_U8) p.gt8 = (const unsigned char*)a->gt; else p.gt = (const long long*)a->gt;
+    p.nc = a->nc; p.kind = a->kind;
     p.nc_pow2 = (a->nc & (a->nc - 1)) == 0;
     p.inv_nc = 1.0f / (float)a->nc;
     p.invN = 1.0f / ((float)a->H * (float)a->W);
     p.out_f = a->warp_out; p.Lb = a->L_b; p.J = a->dLb_dtheta;
-    p.vec4 = (a->W % 4 == 0) && aligned16(a->gt) && (!a->warp_out || aligned16(a->warp_out));
+    p.vec4 = (a->W % 4 == 0) && (a->gt_dtype == SFH_GT_U8 ? (((uintptr_t)a->gt & 3u) == 0) : aligned16(a->gt)) &&
+             (!a->warp_out || aligned16(a->warp_out));
     const bool poi_tail = a->court_poi != nullptr;
     if (poi_tail) {
         if (a->N <= 0 || !a->poi_out) return SFH_E_BADARG;
@@ -1433,14 +1451,14 @@ int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* a
     p.weights = a->weights; p.w_f64 = a->weights_f64; p.w_outer = a->weights_outer;
     p.rec_lambda = a->rec_lambda; p.reproj_lambda = a->reproj_lambda;
     p.loss_out = a->loss_out; p.dtheta_total = a->dtheta_total;
-    if (p.rows_per_warp > 8) {               // keep the staged gt tile <= 64 KiB per CTA
+    if (p.rows_per_warp > 8 && !p.gt8) {     // keep the staged int64 gt tile <= 64 KiB per CTA
         p.rows_per_warp = 8;
         p.ntiles = ((a->W + kTileW - 1) / kTileW) * ((a->H + 63) / 64);
     }
     // experimental persistent warp-specialised variant (opt-in until it beats k_fused: with 3 x 64 KiB
     // gt stages the L1 carve-out left for the template taps is too small — see DESIGN.md §4)
     static const bool persist = getenv("SFH_PERSISTENT") != nullptr;
-    if (persist) {
+    if (persist && !p.gt8) {
         // persistent warp-specialised kernel: 128 x 64 tiles, one CTA per SM
         FusedParams q = p;
         q.rows_per_warp = kPR;

@@ -97,6 +97,7 @@ def _launch_train_tail(stage, theta9, gt_masks, kind, want_mask, gt_poi, nonzero
     a = _lib.SfhTrainTailArgs()
     a.theta, a.xs, a.ys, a.gt = theta9.data_ptr(), xs.data_ptr(), ys.data_ptr(), gt_masks.data_ptr()
     a.B, a.H, a.W, a.nc, a.kind, a.N = B, H, W, stage.mask_classes, _lib.LOSS[kind], N
+    a.gt_dtype = 1 if gt_masks.dtype == torch.uint8 else 0
     a.warp_out, a.L_b, a.dLb_dtheta = _ptr(warp_out), Lb.data_ptr(), J.data_ptr()
     if with_poi:
         a.court_poi, a.court_poi_bstride, a.poi_out = stage.court_poi.data_ptr(), stage.poi_bstride, poi.data_ptr()
@@ -283,8 +284,8 @@ class STNWarpStage(torch.nn.Module):
             raise NotImplementedError(rec_loss)
         theta9 = check_theta(theta, self.device)
         B = theta9.shape[0]
-        if gt_masks.dtype != torch.int64 or gt_masks.device != self.device:
-            raise TypeError("gt_masks must be an int64 tensor on the stage's device (utils/dataset.py:167)")
+        if gt_masks.dtype not in (torch.int64, torch.uint8) or gt_masks.device != self.device:
+            raise TypeError("gt_masks must be an int64 (utils/dataset.py:167) or uint8 tensor on the stage's device")
         if tuple(gt_masks.shape) != (B, self.height, self.width):
             raise ValueError(f"gt_masks must be [B,{self.height},{self.width}], got {tuple(gt_masks.shape)}")
         gt_masks = gt_masks.contiguous()

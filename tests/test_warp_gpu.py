@@ -283,6 +283,11 @@ def test_fused_train_tail_matches_oracle(W, H, B, fam, kind):
     assert np.abs(r["poi"].detach().cpu().numpy() - p64).max() * W <= TOL_POI_PX
     Rb = co.reproj_per_sample(p64, gt_poi, nz, num)
     np.testing.assert_allclose(r["reproj_per_sample"].detach().cpu().numpy(), Rb, rtol=1e-5)
+    # uint8 masks at the surface are the same computation on 1/8 of the bytes
+    r8 = st.train_step(th.to(DEV), cu(gt.astype(np.uint8)), torch.ones(B, dtype=torch.float64, device=DEV), kind)
+    r64 = st.train_step(th.to(DEV), cu(gt), torch.ones(B, dtype=torch.float64, device=DEV), kind)
+    assert torch.equal(r8["rec_per_sample"], r64["rec_per_sample"]) and torch.equal(r8["dtheta"], r64["dtheta"])
+    assert torch.equal(r8["warp_mask"], r64["warp_mask"]) and torch.equal(r8["loss"], r64["loss"])
     # the same loss without materialising the mask must give the same numbers
     r2 = st.train_tail(th.to(DEV), cu(gt), kind, want_mask=False)
     assert torch.equal(r2["rec_per_sample"], r["rec_per_sample"].detach())

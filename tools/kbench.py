@@ -65,6 +65,9 @@ for (W, H, B) in cfgs:
         run(f"store_bilinear_{W}x{H}_B{B}", lambda i: stb.warp(S(i)["th"]), px * 4)
         run(f"store_nearest_{W}x{H}_B{B}", lambda i: stn.warp(S(i)["th"]), px * 4)
         run(f"train_{W}x{H}_B{B}", lambda i: stb.train_step(S(i)["th"], S(i)["gt"], S(i)["w"], "MSE", S(i)["gt_poi"], S(i)["nz"], S(i)["num"], 1.0, 8.0, True, S(i)["out"]), px * 12)
+        for s_ in sets:
+            s_["gt8"] = s_["gt"].to(torch.uint8)
+        run(f"train_u8gt_{W}x{H}_B{B}", lambda i: stb.train_step(S(i)["th"], S(i)["gt8"], S(i)["w"], "MSE", S(i)["gt_poi"], S(i)["nz"], S(i)["num"], 1.0, 8.0, True, S(i)["out"]), px * 5)
         run(f"train_nomask_{W}x{H}_B{B}", lambda i: stb.train_step(S(i)["th"], S(i)["gt"], S(i)["w"], "MSE", S(i)["gt_poi"], S(i)["nz"], S(i)["num"], 1.0, 8.0, False, S(i)["out"]), px * 8)
         run(f"predict_{W}x{H}_B{B}", lambda i: stn.predict_tail(S(i)["th"], S(i)["logits"], True, True, S(i)["outp"]), px * 4 + B * 4 * 360 * 640 * 4)
         run(f"predict_noscore_{W}x{H}_B{B}", lambda i: stn.predict_tail(S(i)["th"], None, False, False, S(i)["outp"]), px * 4)
