@@ -1167,6 +1167,7 @@ __global__ void k_sat_cols(unsigned* S, int sp, int rows, int cols) {
 // host side
 // ------------------------------------------------------------------------------------------
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+constexpr int64_t kTicketBytes = 262400;   // (65535 + 3) int32 tickets, 256-aligned
 
 static int check_template(const sfh_template* t) {
     if (!t || !t->data || t->height <= 0 || t->width <= 0) return SFH_E_BADARG;
@@ -1204,8 +1205,10 @@ static inline bool aligned16(const void* q) { return ((uintptr_t)q & 15u) == 0; 
 static int setup_ws(FusedParams& p, void* ws, int64_t ws_bytes) {
     const int64_t need = sfh_workspace_bytes(p.B, p.H, p.W);
     if (!ws || ws_bytes < need) return SFH_E_WS;
+    // tickets live in a FIXED-size area at the front (B <= 65535 samples + 3): only this area has to
+    // stay zero between calls, so later calls with another B never read stale contrib/partials as tickets
     p.counters = (int*)ws;                                             // [B+3]: samples, batch, tile ticket, done
-    p.contrib = (double*)((char*)ws + align_up((int64_t)(p.B + 3) * 4, 256));   // [B]
+    p.contrib = (double*)((char*)ws + kTicketBytes);                   // [B]
     p.partials = (float*)((char*)p.contrib + align_up((int64_t)p.B * 8, 256));
     const int64_t tx = (p.W + kTileW - 1) / kTileW;
     const int64_t ntiles = tx * ((p.H + kWarps - 1) / kWarps);
@@ -1363,7 +1366,7 @@ int64_t sfh_workspace_bytes(int B, int H, int W) {
     const int64_t nslots = ((tx * ((H + 8 * kPR - 1) / (8 * kPR)) + kPChunk - 1) / kPChunk) * kPCons;   // k_train_persistent
     const int64_t n = ntiles > nslots ? ntiles : nslots;
     const int64_t lists = (int64_t)B * tx * ((H + 8 * kPR - 1) / (8 * kPR)) * kPItems * 2;   // patch lists, 64 B per tile
-    return align_up((int64_t)(B + 3) * 4, 256) + align_up((int64_t)B * 8, 256) +
+    return kTicketBytes + align_up((int64_t)B * 8, 256) +
            align_up((int64_t)B * n * kNPart * 4, 256) + lists;
 }
 

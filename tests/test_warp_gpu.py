@@ -485,6 +485,23 @@ def test_nonfinite_and_degenerate_theta():
     assert np.abs(out - ref).max() <= TOL_MASK
 
 
+def test_workspace_reuse_across_batch_sizes():
+    """One workspace serves calls with different B / sizes: stale per-sample sums of an earlier call
+    must never be read as tickets by a later one (regression: loss was left unwritten)."""
+    tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 1)
+    st = mk_stage(tmpl.to(DEV), poi.to(DEV), (640, 360), 4)
+    ref = {}
+    for B in (6, 64, 3, 64, 17, 6):
+        th = synth.theta_family_a(B, 7).to(DEV)
+        gt = torch.zeros(B, 360, 640, dtype=torch.int64, device=DEV)
+        w = torch.rand(B, 1, generator=torch.Generator().manual_seed(B)).to(DEV)      # [B,1]: the quirk path
+        r = st.train_step(th, gt, w, "MSE")
+        expect = float((r["rec_per_sample"].double().mean() * w.double().mean()))
+        assert abs(float(r["loss"]) - expect) <= 1e-6 * abs(expect), (B, float(r["loss"]), expect)
+        ref.setdefault(B, float(r["loss"]))
+        assert ref[B] == float(r["loss"])
+
+
 # ---------------------------------------------------------------------- API / error conventions
 def test_error_conventions_and_state_dict():
     tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 2)
