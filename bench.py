@@ -430,6 +430,12 @@ def main_ours(args):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent on this box"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath)).get(args.workload)
+            if tj:
+                traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
         frames = wl.B * world
         step_bytes = wl.B * wl.bytes_per_frame
         achieved = step_bytes / (kern_us * 1e-6) / 1e9
@@ -449,7 +455,7 @@ def main_ours(args):
                                          "note": "same call with uint8 gt masks at the surface (SURVEY §8 f-1, opt-in)"}},
             "gpu_launches": args.steps * wl.launches_per_step(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "sfh::k_fused",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "sfh::k_fused",
                          "kernel_us": kern_us, "algorithmic_bytes_per_launch": step_bytes,
                          "bytes_per_frame": wl.bytes_per_frame},
         }
