@@ -31,7 +31,6 @@ struct FusedParams {
     int rows_per_warp;   // R: a CTA covers 128 x 8R output pixels = 8R patches of 16 x 8
     int ntiles;          // CTAs per sample
     int vec4;            // W % 4 == 0 and all row bases 16-byte aligned
-    int uniform_first;   // patch list order (experiment)
     int use_tma;         // the CTA's gt tile (loss) / logits tile (predict) is staged in smem by one TMA load
     // kEpiStore / kEpiBwd
     float* out_f;        // [B,C,H,W]
@@ -192,26 +191,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE_%=:\n\t}"
         :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar, uint64_t pol) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
-        :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
 
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int x, int y, int z, int w, uint64_t* bar, uint64_t pol) {
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int x, int y, int z, int w, uint64_t* bar) {
     asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
-        :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(w), "r"(smem_u32(bar)), "l"(pol) : "memory");
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(w), "r"(smem_u32(bar)) : "memory");
 }
 
 // Reduce 16 per-lane values across the warp with 16 shuffles: after the butterfly, lane L holds
@@ -263,28 +252,17 @@ constexpr float kBoxMargin = 1.0f / 64.0f;   // slack (in texels) on the patch b
 // kernel entry, so it streams in behind the classification prologue and the pixel loop never
 // waits on a global load.
 // ------------------------------------------------------------------------------------------
-#ifdef SFH_TIMELINE
-__device__ long long* g_timeline = nullptr;      // [ctas][8] globaltimer stamps (debug builds only)
-__device__ __forceinline__ void tl_stamp(int cta, int phase) {
-    if (g_timeline && threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_timeline[(size_t)cta * 8 + phase] = (long long)t;
-    }
-}
-#define SFH_TL(phase) tl_stamp((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, phase)
-#else
-#define SFH_TL(phase)
-#endif
-
 template <int FMT, int MODE, int EPI, bool FT>
 __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(128) unsigned char s_dyn[];            // TMA destination (gt tile)
     __shared__ __align__(16) float s_tab[Taps<FMT>::kSmemFloats];
+    __shared__ float s_red[kWarps][16];
+    __shared__ double s_fin[kNPart][kFinGroup];
     __shared__ float s_gx[kMaxR + 1][kWarps + 1], s_gy[kMaxR + 1][kWarps + 1], s_gz[kMaxR + 1][kWarps + 1];
     __shared__ unsigned short s_items[kMaxR * kWarps];   // patch id | (class+1) << 8, edge patches first
     __shared__ int s_ecnt[kWarps];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_last;
 
     const int b = blockIdx.z, tx = blockIdx.x, ty = blockIdx.y;
     const int tile = ty * gridDim.x + tx;
@@ -297,20 +275,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
     const bool tma = (EPI == kEpiLoss || EPI == kEpiPredict) && p.use_tma;
 
-    SFH_TL(0);
-    if (tma && threadIdx.x == 0) {
-        // the tile's streaming input is requested before anything else so that it arrives behind
-        // the whole prologue (evict-first in L2: it is read exactly once)
-        mbar_init(&s_bar, 1);
-        const uint64_t pol = l2_policy_evict_first();
-        if (EPI == kEpiLoss) {
-            mbar_expect_tx(&s_bar, (uint32_t)(R * 8 * kTileW * (p.gt8 ? 1 : sizeof(long long))));
-            tma_load_3d(s_dyn, &p.gt_map, tx * kTileW, band0, b, &s_bar, pol);
-        } else {                             // logits [B,4,h,w]: 64 x 4R x 4 floats under this 128 x 8R tile
-            mbar_expect_tx(&s_bar, (uint32_t)(R * 4 * (kTileW / 2) * 4 * sizeof(float)));
-            tma_load_4d(s_dyn, &p.gt_map, tx * (kTileW / 2), band0 >> 1, 0, b, &s_bar, pol);
-        }
-    }
+    if (tma && threadIdx.x == 0) mbar_init(&s_bar, 1);
     Taps<FMT> taps;
     taps.build_tables(p.t, s_tab);
     if ((EPI == kEpiLoss || EPI == kEpiPredict) && tile == 0 && p.poi.court_poi)
@@ -331,7 +296,15 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         s_gz[r][k] = f.zok ? __fdividef(1.0f, f.s) : __int_as_float(0x7fc00000);   // sign of Z; NaN poisons the patch
     }
     __syncthreads();                         // s_bar initialised, tables and corner grid written
-    SFH_TL(1);
+    if (tma && threadIdx.x == 0) {
+        if (EPI == kEpiLoss) {
+            mbar_expect_tx(&s_bar, (uint32_t)(R * 8 * kTileW * (p.gt8 ? 1 : sizeof(long long))));
+            tma_load_3d(s_dyn, &p.gt_map, tx * kTileW, band0, b, &s_bar);
+        } else {                             // logits [B,4,h,w]: 64 x 4R x 4 floats under this 128 x 8R tile
+            mbar_expect_tx(&s_bar, (uint32_t)(R * 4 * (kTileW / 2) * 4 * sizeof(float)));
+            tma_load_4d(s_dyn, &p.gt_map, tx * (kTileW / 2), band0 >> 1, 0, b, &s_bar);
+        }
+    }
     taps.init(p.t, b, s_tab);
     int cls = -1;
     if (classify && threadIdx.x < nitems) {
@@ -376,10 +349,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             total += c;
             if (w < warp) before += c;
         }
-        static_assert(true, "");
-        int pos;
-        if (p.uniform_first) pos = is_edge ? (nitems - total) + before : ((int)threadIdx.x - before);
-        else pos = is_edge ? before : total + ((int)threadIdx.x - before);
+        const int pos = is_edge ? before : total + ((int)threadIdx.x - before);
         s_items[pos] = (unsigned short)(threadIdx.x | ((cls + 1) << 8));
     }
     __syncthreads();
@@ -393,9 +363,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     const float ncf = (float)p.nc;
     const long long* s_gt = reinterpret_cast<const long long*>(s_dyn);
 
-    SFH_TL(2);
     if (tma) mbar_wait(&s_bar, 0);           // gt tile has landed (it streamed in behind the prologue)
-    SFH_TL(3);
 
 #pragma unroll 1
     for (int it = warp; it < nitems; it += kWarps) {
@@ -638,13 +606,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 
     if (EPI == kEpiStore) return;
     if (EPI == kEpiPredict && !(p.score && p.ratio != 0)) return;
-    SFH_TL(4);
 
-    // ------- per-sample reduction: lane -> warp (16-value butterfly) -> one slot per warp ---------
-    // Every warp publishes its sums and takes its own release ticket, so the CTA ends without a
-    // barrier; the warp that takes the sample's last ticket adds all slots in fixed order in fp64.
+    // ---------------- per-sample reduction: lane -> warp -> CTA partial -> last CTA -----------
     if (EPI == kEpiLoss && p.kind != SFH_LOSS_MSE) loss_sum *= 0.5f;
-    const int nslots = p.ntiles * kWarps;
     {
         float vals[16];
         vals[0] = loss_sum;
@@ -654,50 +618,49 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 #pragma unroll
         for (int k = 11; k < 16; ++k) vals[k] = 0.f;
         const float tot = warp_reduce16(vals, lane);
-        const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-        if (!(lane & 1) && idx < kNPart)
-            __stcg(p.partials + ((size_t)b * nslots + (size_t)tile * kWarps + warp) * kNPart + idx, tot);
+        if (!(lane & 1)) s_red[warp][((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = tot;
     }
-    __syncwarp();
-    SFH_TL(5);
-    int last = 0;
-    if (lane == 0) last = (ticket_release(p.counters + b) == nslots - 1);
-    SFH_TL(6);
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (!last) return;
-    __threadfence();   // acquire side, once per sample
-    double sum[kNPart];
+    __syncthreads();
+    if (threadIdx.x < kNPart) {
+        float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kNPart; ++k) sum[k] = 0.0;
+        for (int w = 0; w < kWarps; ++w) s += s_red[w][threadIdx.x];
+        __stcg(p.partials + ((size_t)b * p.ntiles + tile) * kNPart + threadIdx.x, s);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (ticket_release(p.counters + b) == p.ntiles - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();   // acquire side, once per sample
     {
-        const float* base = p.partials + (size_t)b * nslots * kNPart;
-        for (int q = lane; q < nslots; q += 32) {
-            const float4* r4 = reinterpret_cast<const float4*>(base + (size_t)q * kNPart);
-            const float4 a0 = __ldcg(r4), a1 = __ldcg(r4 + 1), a2 = __ldcg(r4 + 2);
-            sum[0] += a0.x; sum[1] += a0.y; sum[2] += a0.z; sum[3] += a0.w;
-            sum[4] += a1.x; sum[5] += a1.y; sum[6] += a1.z; sum[7] += a1.w;
-            sum[8] += a2.x; sum[9] += a2.y; sum[10] += a2.z; sum[11] += a2.w;
+        const int k = threadIdx.x / kFinGroup, jj = threadIdx.x % kFinGroup;
+        if (k < kNPart) {
+            double s = 0.0;
+            const float* base = p.partials + (size_t)b * p.ntiles * kNPart + k;
+            for (int t = jj; t < p.ntiles; t += kFinGroup) s += (double)__ldcg(base + (size_t)t * kNPart);
+            s_fin[k][jj] = s;
         }
     }
+    __syncthreads();
+    if (threadIdx.x < kNPart) {
+        const int k = threadIdx.x;
+        double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < kNPart - 1; ++k) {
-        if (EPI == kEpiBwd && (k == 0 || k == 10)) continue;
-        if (EPI == kEpiLoss && k == 10) continue;
-        if (EPI == kEpiPredict && k != 10) continue;
-        sum[k] = warp_sum(sum[k]);
+        for (int jj = 0; jj < kFinGroup; ++jj) s += s_fin[k][jj];
+        if (EPI == kEpiBwd) {
+            if (k >= 1 && k <= 9) p.dtheta[9 * b + k - 1] = (float)s;
+        } else if (EPI == kEpiLoss) {
+            if (k == 0) { s = s / ((double)H * (double)W); p.Lb[b] = (float)s; }
+            else if (k <= 9) p.J[9 * b + k - 1] = (float)s;
+            s_fin[k][0] = s;
+        } else if (EPI == kEpiPredict) {
+            if (k == 10) p.score[b] = (float)(s / ((double)p.lh * (double)p.lw));
+        }
     }
-    if (EPI == kEpiBwd) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) if (lane == k) p.dtheta[9 * b + k] = (float)sum[1 + k];
-    } else if (EPI == kEpiPredict) {
-        if (lane == 0) p.score[b] = (float)(sum[10] / ((double)p.lh * (double)p.lw));
-    } else if (EPI == kEpiLoss) {
-        const double Lb = sum[0] / ((double)H * (double)W);
-        if (lane == 0) p.Lb[b] = (float)Lb;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) if (lane == k) p.J[9 * b + k] = (float)sum[1 + k];
-        if (p.loss_out) {
-            // ---- weighting + batch mean + total dtheta, still inside the same launch ----------
+    if (EPI == kEpiLoss && p.loss_out) {
+        // ---- weighting + batch mean + total dtheta, still inside the same launch ------------
+        __syncthreads();
+        if (warp == 0) {
             const int B = p.B;
             double w_eff = 1.0;
             if (p.weights) {
@@ -712,30 +675,27 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             }
             const bool rep = p.poi.gt_poi != nullptr;
             const double cr = (double)p.rec_lambda * w_eff, cp = (double)p.reproj_lambda;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                if (lane == k) {
-                    const double Kk = rep ? (double)__ldcg(p.poi.K + 9 * b + k) : 0.0;
-                    p.dtheta_total[9 * b + k] = (float)((cr * sum[1 + k] + cp * Kk) / (double)B);
-                }
+            if (lane < 9) {
+                const double Kk = rep ? (double)__ldcg(p.poi.K + 9 * b + lane) : 0.0;
+                p.dtheta_total[9 * b + lane] = (float)((cr * s_fin[1 + lane][0] + cp * Kk) / (double)B);
             }
             int last2 = 0;
             if (lane == 0) {
                 const double Rv = rep ? (double)__ldcg(p.poi.Rb + b) : 0.0;
-                __stcg(p.contrib + b, cr * Lb + cp * Rv);
+                __stcg(p.contrib + b, cr * s_fin[0][0] + cp * Rv);
                 last2 = (ticket_release(p.counters + B) == B - 1);
             }
             last2 = __shfl_sync(0xffffffffu, last2, 0);
             if (last2) {                    // last sample of the batch: fixed-order sum over b
                 __threadfence();
-                double sb = 0.0;
-                for (int i = lane; i < B; i += 32) sb += __ldcg(p.contrib + i);
-                sb = warp_sum(sb);
-                if (lane == 0) { *p.loss_out = (float)(sb / (double)B); p.counters[B] = 0; }
+                double s = 0.0;
+                for (int i = lane; i < B; i += 32) s += __ldcg(p.contrib + i);
+                s = warp_sum(s);
+                if (lane == 0) { *p.loss_out = (float)(s / (double)B); p.counters[B] = 0; }
             }
         }
     }
-    if (lane == 0) p.counters[b] = 0;   // leave the ticket area zeroed for the next call
+    if (threadIdx.x == 0) p.counters[b] = 0;   // leave the workspace zeroed for the next call
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1238,8 +1198,6 @@ static void fill_common(FusedParams& p, const float* theta, const sfh_template* 
         while (R > 1 && (int64_t)tiles_x * ((H + kWarps * R - 1) / (kWarps * R)) * B < 4 * 3 * 148) R >>= 1;
     p.rows_per_warp = R;
     p.ntiles = tiles_x * ((H + kWarps * R - 1) / (kWarps * R));
-    static const int uf = getenv("SFH_UNIFORM_FIRST") ? 1 : 0;
-    p.uniform_first = uf;
 }
 
 static inline bool aligned16(const void* q) { return ((uintptr_t)q & 15u) == 0; }
@@ -1253,7 +1211,7 @@ static int setup_ws(FusedParams& p, void* ws, int64_t ws_bytes) {
     p.contrib = (double*)((char*)ws + kTicketBytes);                   // [B]
     p.partials = (float*)((char*)p.contrib + align_up((int64_t)p.B * 8, 256));
     const int64_t tx = (p.W + kTileW - 1) / kTileW;
-    const int64_t ntiles = tx * ((p.H + kWarps - 1) / kWarps) * kWarps;
+    const int64_t ntiles = tx * ((p.H + kWarps - 1) / kWarps);
     const int64_t nslots = ((tx * ((p.H + 8 * kPR - 1) / (8 * kPR)) + kPChunk - 1) / kPChunk) * kPCons;
     const int64_t n = ntiles > nslots ? ntiles : nslots;
     p.lists = (unsigned short*)((char*)p.partials + align_up((int64_t)p.B * n * kNPart * 4, 256));
@@ -1383,12 +1341,6 @@ using namespace sfh;
 
 extern "C" {
 
-#ifdef SFH_TIMELINE
-int sfh_debug_set_timeline(long long* buf) {     // debug builds only; not part of the shipped ABI
-    return (int)cudaMemcpyToSymbol(g_timeline, &buf, sizeof(buf));
-}
-#endif
-
 int sfh_abi_version(void) { return SFH_ABI_VERSION; }
 
 const char* sfh_build_info(void) {
@@ -1410,7 +1362,7 @@ const char* sfh_error_string(int code) {
 int64_t sfh_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     const int64_t tx = (W + kTileW - 1) / kTileW;
-    const int64_t ntiles = tx * ((H + kWarps - 1) / kWarps) * kWarps;             // k_fused: 8 warp slots per tile, R = 1 upper bound
+    const int64_t ntiles = tx * ((H + kWarps - 1) / kWarps);                      // k_fused, R = 1 upper bound
     const int64_t nslots = ((tx * ((H + 8 * kPR - 1) / (8 * kPR)) + kPChunk - 1) / kPChunk) * kPCons;   // k_train_persistent
     const int64_t n = ntiles > nslots ? ntiles : nslots;
     const int64_t lists = (int64_t)B * tx * ((H + 8 * kPR - 1) / (8 * kPR)) * kPItems * 2;   // patch lists, 64 B per tile
