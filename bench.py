@@ -45,6 +45,10 @@ WORKLOADS = {
     "c3": (1280, 720, 15, "ncaa_nc4", "predict",
            "C3 predict tail 1280x720 batch 15: nearest warp -> int32 mask + CE consistency vs logits [4,360,640] + POI",
            1280 * 720 * 4 + 4 * 360 * 640 * 4),
+    "c5": (1280, 720, 256, "ncaa_nc4", "predict",
+           "C5 video-scale sweep: one step = one micro-batch of 256 frames of C3 work (65,536 frames = 256 steps / n_gpus per rank); "
+           "output/logit buffers reused, batch-sharded, per-step all-reduce of the score sum",
+           1280 * 720 * 4 + 4 * 360 * 640 * 4),
     "c4": (1280, 720, 32, "pitch_v3_nc4", "fwd",
            "C4 pitch v3 HD template bilinear forward 1280x720 batch 32 + POI", 1280 * 720 * 4),
 }
@@ -259,9 +263,12 @@ def time_workload(wl, steps, warmup, use_graph, dist_vec=None):
 
     def one(i):
         r = wl.step(i)
-        if multi and isinstance(r, dict) and "loss" in r:
+        if multi and isinstance(r, dict) and ("loss" in r or "consist_score" in r):
             slot = dist_vec[i % dist_vec.shape[0]]
-            slot[0].copy_(r["loss"])           # local mean loss (equal shard sizes); [1] carries the frame count
+            if "loss" in r:
+                slot[0].copy_(r["loss"])       # local mean loss (equal shard sizes); [1] carries the frame count
+            else:
+                slot[0].copy_(r["consist_score"].sum())   # metric numerator of the inference sweep
             # global loss numerator + frame count.  Nothing on the next step depends on it,
             # so the all-reduce runs beside the next step's kernel and is joined once per buffer rotation.
             pending.append(dist.all_reduce(slot, async_op=True))
@@ -482,7 +489,7 @@ def main_ours(args):
                                     if k in ("value", "unit", "cores", "kind", "sample")}
             extra = {}
             for name in WORKLOADS:
-                if name == args.workload:
+                if name == args.workload or name == "c5":
                     continue
                 try:
                     w2 = Workload(name, dev, seed=7)
