@@ -262,6 +262,21 @@ constexpr float kBoxMargin = 1.0f / 64.0f;   // slack (in texels) on the patch b
 // kernel entry, so it streams in behind the classification prologue and the pixel loop never
 // waits on a global load.
 // ------------------------------------------------------------------------------------------
+#ifdef SFH_TIMELINE
+// Development aid (tools/timeline.py): per-CTA globaltimer stamps at the phase boundaries.
+__device__ long long* g_timeline = nullptr;      // [ctas][8]
+__device__ __forceinline__ void tl_stamp(int cta, int phase) {
+    if (g_timeline && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_timeline[(size_t)cta * 8 + phase] = (long long)t;
+    }
+}
+#define SFH_TL(phase) tl_stamp((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, phase)
+#else
+#define SFH_TL(phase)
+#endif
+
 template <int FMT, int MODE, int EPI, bool FT>
 __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(128) unsigned char s_dyn[];            // TMA destination (gt tile)
@@ -285,6 +300,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
     const bool tma = (EPI == kEpiLoss || EPI == kEpiPredict) && p.use_tma;
 
+    SFH_TL(0);
     if (tma && threadIdx.x == 0) {
         // the tile's streaming input is requested before anything else so that it arrives behind
         // the whole prologue (evict-first in L2: it is read exactly once)
@@ -318,6 +334,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         s_gz[r][k] = f.zok ? __fdividef(1.0f, f.s) : __int_as_float(0x7fc00000);   // sign of Z; NaN poisons the patch
     }
     __syncthreads();                         // s_bar initialised, tables and corner grid written
+    SFH_TL(1);
     taps.init(p.t, b, s_tab);
     int cls = -1;
     if (classify && threadIdx.x < nitems) {
@@ -376,7 +393,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     const float ncf = (float)p.nc;
     const long long* s_gt = reinterpret_cast<const long long*>(s_dyn);
 
+    SFH_TL(2);
     if (tma) mbar_wait(&s_bar, 0);           // gt tile has landed (it streamed in behind the prologue)
+    SFH_TL(3);
 
 #pragma unroll 1
     for (int it = warp; it < nitems; it += kWarps) {
@@ -619,6 +638,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 
     if (EPI == kEpiStore) return;
     if (EPI == kEpiPredict && !(p.score && p.ratio != 0)) return;
+    SFH_TL(4);
 
     // ---------------- per-sample reduction: lane -> warp -> CTA partial -> last CTA -----------
     if (EPI == kEpiLoss && p.kind != SFH_LOSS_MSE) loss_sum *= 0.5f;
@@ -641,7 +661,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         __stcg(p.partials + ((size_t)b * p.ntiles + tile) * kNPart + threadIdx.x, s);
     }
     __syncthreads();
+    SFH_TL(5);
     if (threadIdx.x == 0) s_last = (ticket_release(p.counters + b) == p.ntiles - 1);
+    SFH_TL(6);
     __syncthreads();
     if (!s_last) return;
     __threadfence();   // acquire side, once per sample
@@ -1353,6 +1375,12 @@ static bool make_logits_map(FusedParams& p) {
 using namespace sfh;
 
 extern "C" {
+
+#ifdef SFH_TIMELINE
+int sfh_debug_set_timeline(long long* buf) {     // debug builds only; not part of the shipped ABI
+    return (int)cudaMemcpyToSymbol(g_timeline, &buf, sizeof(buf));
+}
+#endif
 
 int sfh_abi_version(void) { return SFH_ABI_VERSION; }
 
