@@ -506,10 +506,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             }
         }
         Pix px[4];
+        if (EPI != kEpiLoss) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)          // u*h{0,3,6}: the first product of the bmm chain
-            px[j] = pixel_geom<MODE>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]), __fmul_rn(u[j], Hm.h[6]),
-                                     v, Wc_f, Hc_f);
+            for (int j = 0; j < 4; ++j)      // u*h{0,3,6}: the first product of the bmm chain
+                px[j] = pixel_geom<MODE>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]), __fmul_rn(u[j], Hm.h[6]),
+                                         v, Wc_f, Hc_f);
+        }
 
         if (EPI == kEpiStore || EPI == kEpiBwd) {
             float gix[4] = {0.f, 0.f, 0.f, 0.f}, giy[4] = {0.f, 0.f, 0.f, 0.f};
@@ -554,45 +556,41 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         }
 
         if (EPI == kEpiLoss) {
+            // one pixel at a time, start to finish (geometry -> taps -> value -> loss -> chain rule):
+            // only o[j] crosses iterations, which keeps the live state small enough for 4 CTAs/SM
             float o[4];
-            TapVals t[4];
+            bool any = false;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                t[j] = taps.fetch4(0, px[j].x0, px[j].y0);
-                o[j] = bilerp(px[j], t[j]);
+                const Pix q = pixel_geom<MODE>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]),
+                                               __fmul_rn(u[j], Hm.h[6]), v, Wc_f, Hc_f);
+                const TapVals t = taps.fetch4(0, q.x0, q.y0);
+                o[j] = bilerp(q, t);
+                const float d = o[j] - tgt[j];
+                float l, g;
+                if (p.kind == SFH_LOSS_MSE || fabsf(d) < 1.0f) {   // MSE d^2 ; SmoothL1(beta=1) 0.5 d^2
+                    l = d * d; g = d;
+                } else {
+                    l = 2.0f * fabsf(d) - 1.0f; g = d > 0.f ? 1.0f : -1.0f;   // doubled, halved below
+                }
+                if (!SFH_PIX_OK(j)) { l = 0.f; g = 0.f; }
+                loss_sum += l;
+                // the gradient lives on footprints that straddle a class edge; a uniform footprint
+                // cancels exactly (a*sy - a*sy), so the warp skips the chain rule for every pixel slot
+                // on which no lane straddles one (a vertical court line touches 1-2 of the 4 slots)
+                if (__any_sync(0xffffffffu, !t.uni)) {
+                    g *= gscale;
+                    const float gix = ((t.b - t.a) * q.sy + (t.d - t.c) * q.ny) * g;
+                    const float giy = ((t.c - t.a) * q.ex + (t.d - t.b) * q.wx) * g;
+                    acc.add(q, gix, giy, halfWc, halfHc, u[j]);
+                    any = true;
+                }
             }
             if (p.out_f) {
                 if (vec) __stcs((float4*)(p.out_f + rowbase), make_float4(o[0], o[1], o[2], o[3]));
                 else
 #pragma unroll
                     for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_f[rowbase + j] = o[j];
-            }
-            float g[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float d = o[j] - tgt[j];
-                float l;
-                if (p.kind == SFH_LOSS_MSE || fabsf(d) < 1.0f) {   // MSE d^2 ; SmoothL1(beta=1) 0.5 d^2
-                    l = d * d; g[j] = d;
-                } else {
-                    l = 2.0f * fabsf(d) - 1.0f; g[j] = d > 0.f ? 1.0f : -1.0f;   // doubled, halved below
-                }
-                if (!SFH_PIX_OK(j)) { l = 0.f; g[j] = 0.f; }
-                loss_sum += l;
-                g[j] *= gscale;
-            }
-            // the gradient lives on footprints that straddle a class edge; a uniform footprint
-            // cancels exactly (a*sy - a*sy), so the warp skips the chain rule for every pixel slot j
-            // on which no lane straddles one (a vertical court line touches 1-2 of the 4 slots)
-            bool any = false;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (__any_sync(0xffffffffu, !t[j].uni)) {
-                    const float gix = ((t[j].b - t[j].a) * px[j].sy + (t[j].d - t[j].c) * px[j].ny) * g[j];
-                    const float giy = ((t[j].c - t[j].a) * px[j].ex + (t[j].d - t[j].b) * px[j].wx) * g[j];
-                    acc.add(px[j], gix, giy, halfWc, halfHc, u[j]);
-                    any = true;
-                }
             }
             if (any) acc.end_row(v);
         }
