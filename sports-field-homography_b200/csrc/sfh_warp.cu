@@ -289,6 +289,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_last;
 
+    // the loss epilogue always samples bilinearly; its MODE argument carries the criterion instead
+    constexpr int SMODE = (EPI == kEpiLoss) ? SFH_MODE_BILINEAR : MODE;
+    constexpr bool kMse = (EPI != kEpiLoss) || (MODE == SFH_LOSS_MSE);
     const int b = blockIdx.z, tx = blockIdx.x, ty = blockIdx.y;
     const int tile = ty * gridDim.x + tx;
     const int H = p.H, W = p.W;
@@ -385,11 +388,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     __syncthreads();
 
     const int C = (FMT == SFH_TMPL_F32) ? p.t.channels : 1;
+    const size_t base_b = (size_t)b * H * W;
     const float halfWc = 0.5f * Wc_f, halfHc = 0.5f * Hc_f;
     GradAcc acc;
     acc.zero();
     float loss_sum = 0.f, score_sum = 0.f;
-    const float gscale = (p.kind == SFH_LOSS_MSE ? 2.0f : 1.0f) * p.invN;
+    const float gscale = (kMse ? 2.0f : 1.0f) * p.invN;
     const float ncf = (float)p.nc;
     const long long* s_gt = reinterpret_cast<const long long*>(s_dyn);
 
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         const bool row_ok = FT || row < H;
         const int rowc = FT ? row : min(row, H - 1);
         const bool vec = FT || (p.vec4 && row_ok && col + 3 < W);
-        const size_t rowbase = ((size_t)b * H + rowc) * W + col;   // C == 1 offset
+        const size_t rowbase = base_b + (unsigned)(rowc * W + col);     // C == 1 offset (32-bit in-sample part)
 #define SFH_PIX_OK(j) (FT || (row_ok && col + (j) < W))
 
         float tgt[4];
@@ -456,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float d = cval - tgt[j];
-                    float l = (p.kind == SFH_LOSS_MSE || fabsf(d) < 1.0f) ? d * d : 2.0f * fabsf(d) - 1.0f;
+                    float l = (kMse || fabsf(d) < 1.0f) ? d * d : 2.0f * fabsf(d) - 1.0f;
                     if (!SFH_PIX_OK(j)) l = 0.f;
                     loss_sum += l;
                 }
@@ -509,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         if (EPI != kEpiLoss) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)      // u*h{0,3,6}: the first product of the bmm chain
-                px[j] = pixel_geom<MODE>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]), __fmul_rn(u[j], Hm.h[6]),
+                px[j] = pixel_geom<SMODE>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]), __fmul_rn(u[j], Hm.h[6]),
                                          v, Wc_f, Hc_f);
         }
 
@@ -529,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if (MODE == SFH_MODE_NEAREST) {
+                    if (SMODE == SFH_MODE_NEAREST) {
                         o[j] = taps.fetch1(c, px[j].x0, px[j].y0);
                     } else {
                         const TapVals t = taps.fetch4(c, px[j].x0, px[j].y0);
@@ -562,13 +566,13 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             bool any = false;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const Pix q = pixel_geom<MODE>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]),
+                const Pix q = pixel_geom<SMODE>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]),
                                                __fmul_rn(u[j], Hm.h[6]), v, Wc_f, Hc_f);
                 const TapVals t = taps.fetch4(0, q.x0, q.y0);
                 o[j] = bilerp(q, t);
                 const float d = o[j] - tgt[j];
                 float l, g;
-                if (p.kind == SFH_LOSS_MSE || fabsf(d) < 1.0f) {   // MSE d^2 ; SmoothL1(beta=1) 0.5 d^2
+                if (kMse || fabsf(d) < 1.0f) {   // MSE d^2 ; SmoothL1(beta=1) 0.5 d^2
                     l = d * d; g = d;
                 } else {
                     l = 2.0f * fabsf(d) - 1.0f; g = d > 0.f ? 1.0f : -1.0f;   // doubled, halved below
@@ -600,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float o;
-                if (MODE == SFH_MODE_NEAREST) o = taps.fetch1(0, px[j].x0, px[j].y0);
+                if (SMODE == SFH_MODE_NEAREST) o = taps.fetch1(0, px[j].x0, px[j].y0);
                 else o = bilerp(px[j], taps.fetch4(0, px[j].x0, px[j].y0));
                 ci[j] = __float2int_rz(__fmul_rn(o, ncf));   // (warp*nc).int()
             }
@@ -639,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     SFH_TL(4);
 
     // ---------------- per-sample reduction: lane -> warp -> CTA partial -> last CTA -----------
-    if (EPI == kEpiLoss && p.kind != SFH_LOSS_MSE) loss_sum *= 0.5f;
+    if (EPI == kEpiLoss && !kMse) loss_sum *= 0.5f;
     {
         float vals[16];
         vals[0] = loss_sum;
@@ -1511,7 +1515,8 @@ int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* a
         }
     }
     p.use_tma = make_gt_map(p) ? 1 : 0;
-    return launch_fused<SFH_MODE_BILINEAR, kEpiLoss>(p, (cudaStream_t)stream);
+    return a->kind == SFH_LOSS_MSE ? launch_fused<SFH_LOSS_MSE, kEpiLoss>(p, (cudaStream_t)stream)
+                                   : launch_fused<SFH_LOSS_SMOOTHL1, kEpiLoss>(p, (cudaStream_t)stream);
 }
 
 int sfh_predict_tail(const sfh_template* tmpl, const sfh_predict_tail_args* a, void* stream) {
