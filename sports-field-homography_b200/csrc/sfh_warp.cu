@@ -141,6 +141,17 @@ __device__ __forceinline__ float ce4(float l0, float l1, float l2, float l3, int
     return fmaf(__log2f(se), 0.6931471805599453f, mx) - sel;
 }
 
+// CE of the logits pixel this lane owns inside a patch's 4 x 8 logits block (ratio-2 predict path):
+// lane -> (li = lane/8, lj = lane%8); its warp pixel is (row0 + 2*li, col0 + 2*lj).
+template <bool FT>
+__device__ __forceinline__ float ce_patch_lane(const float* s_lg, int cst, int pr, int pk, int lane, int cls,
+                                               int row0, int col0, int H, int W) {
+    const int li = lane >> 3, lj = lane & 7;
+    if (!FT && !(row0 + 2 * li < H && col0 + 2 * lj < W)) return 0.f;
+    const float* sl = s_lg + (pr * 4 + li) * (kTileW / 2) + pk * 8 + lj;
+    return ce4(sl[0], sl[cst], sl[2 * cst], sl[3 * cst], cls);
+}
+
 // log-sum-exp cross entropy of one pixel, nc logits strided by `cs` (F.cross_entropy, reduction none).
 __device__ __forceinline__ float ce_pixel(const float* lg, size_t cs, int nc, int cls) {
     if (nc == 4) return ce4(__ldcs(lg), __ldcs(lg + cs), __ldcs(lg + 2 * cs), __ldcs(lg + 3 * cs), cls);
@@ -477,15 +488,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         if (FT || col + j < W) score_sum += ce_pixel(lg + j, cs, p.nc, ci);
+                } else if (p.score && p.ratio == 2 && tma) {
+                    // staged logits: the patch's 4 x 8 logits pixels are dealt one per lane
+                    score_sum += ce_patch_lane<FT>(reinterpret_cast<const float*>(s_dyn), R * 4 * (kTileW / 2), pr, pk, lane,
+                                                   ci, band0 + pr * 8, tx * kTileW + pk * kPatchW, H, W);
                 } else if (p.score && p.ratio == 2 && row_ok && !(row & 1)) {
-                    if (tma) {
-                        const float* sl = reinterpret_cast<const float*>(s_dyn) + (pr * 4 + (ly >> 1)) * (kTileW / 2) + pk * 8 + lx * 2;
-                        const int cst = R * 4 * (kTileW / 2);
-                        const float2 a0 = *reinterpret_cast<const float2*>(sl), a1 = *reinterpret_cast<const float2*>(sl + cst);
-                        const float2 a2 = *reinterpret_cast<const float2*>(sl + 2 * cst), a3 = *reinterpret_cast<const float2*>(sl + 3 * cst);
-                        if (FT || col < W) score_sum += ce4(a0.x, a1.x, a2.x, a3.x, ci);
-                        if (FT || col + 2 < W) score_sum += ce4(a0.y, a1.y, a2.y, a3.y, ci);
-                    } else {
+                    {
                         const size_t cs = (size_t)p.lh * p.lw;
                         const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)(row >> 1) * p.lw + (col >> 1);
                         if (FT || col < W) score_sum += ce_pixel(lg, cs, p.nc, ci);
@@ -618,16 +626,17 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (FT || col + j < W) score_sum += ce_pixel(lg + j, cs, p.nc, ci[j]);
+            } else if (p.score && p.ratio == 2 && tma) {
+                // F.interpolate(nearest) to (H/2, W/2) picks source pixel (2i, 2j); with the logits
+                // staged in smem the patch's 4 x 8 logits pixels are dealt one per lane, the class of
+                // pixel (2i, 2j) comes from its owner lane by shuffle
+                const int src = ((lane >> 3) << 3) + ((lane & 7) >> 1);       // owner: ly = 2*li, lx = lj/2
+                const int c0 = __shfl_sync(0xffffffffu, ci[0], src), c2 = __shfl_sync(0xffffffffu, ci[2], src);
+                score_sum += ce_patch_lane<FT>(reinterpret_cast<const float*>(s_dyn), R * 4 * (kTileW / 2), pr, pk, lane,
+                                               (lane & 1) ? c2 : c0, band0 + pr * 8, tx * kTileW + pk * kPatchW, H, W);
             } else if (p.score && p.ratio == 2 && row_ok && !(row & 1)) {
                 // F.interpolate(nearest) to (H/2, W/2) picks source pixel (2i, 2j)
-                if (tma) {
-                    const float* sl = reinterpret_cast<const float*>(s_dyn) + (pr * 4 + (ly >> 1)) * (kTileW / 2) + pk * 8 + lx * 2;
-                    const int cst = R * 4 * (kTileW / 2);
-                    const float2 a0 = *reinterpret_cast<const float2*>(sl), a1 = *reinterpret_cast<const float2*>(sl + cst);
-                    const float2 a2 = *reinterpret_cast<const float2*>(sl + 2 * cst), a3 = *reinterpret_cast<const float2*>(sl + 3 * cst);
-                    if (FT || col < W) score_sum += ce4(a0.x, a1.x, a2.x, a3.x, ci[0]);
-                    if (FT || col + 2 < W) score_sum += ce4(a0.y, a1.y, a2.y, a3.y, ci[2]);
-                } else {
+                {
                     const size_t cs = (size_t)p.lh * p.lw;
                     const float* lg = p.logits + (size_t)b * p.nc * cs + (size_t)(row >> 1) * p.lw + (col >> 1);
                     if (FT || col < W) score_sum += ce_pixel(lg, cs, p.nc, ci[0]);
