@@ -46,6 +46,10 @@ extern "C" {
 #define SFH_GT_I64 0   /* int64, what the reference's dataset yields (utils/dataset.py:167) */
 #define SFH_GT_U8  1   /* uint8 class ids: the narrow surface of SURVEY.md §8 f-1 (8x less PCIe / HBM traffic) */
 
+/* dtype of the integer mask written by sfh_predict_tail */
+#define SFH_MASK_I32 0  /* int32, what Reconstructor.predict returns (models/reconstructor.py:240) */
+#define SFH_MASK_U8  1  /* uint8, what predict.py:99 converts it to before it leaves the GPU worker (§8 f-1) */
+
 /* template storage formats */
 #define SFH_TMPL_F32 0  /* [Bt,C,Hc,Wc] fp32 as open_court_template returns it (utils/dataset.py:47-61) */
 #define SFH_TMPL_Q2  1  /* quad-packed palette indices, 2 bits/tap, uint8  [(Hc+2) x pitch] */
@@ -164,13 +168,14 @@ typedef struct sfh_predict_tail_args {
     int32_t h, w;                    /* logits spatial size */
     int32_t N;
     const float* logits;             /* [B,nc,h,w] nullable */
-    int32_t* warp_out;               /* [B,H,W] int32 */
+    void*    warp_out;               /* [B,H,W] int32 (default) or uint8, see mask_dtype */
     float*  score;                   /* [B] nullable */
     const float* court_poi;          /* nullable */
     int64_t court_poi_bstride;
     float*  poi_out;                 /* [B,N,2] */
     void*   workspace;
     int64_t workspace_bytes;
+    int32_t mask_dtype;              /* SFH_MASK_I32 (default 0) | SFH_MASK_U8 */
 } sfh_predict_tail_args;
 
 int sfh_predict_tail(const sfh_template* tmpl, const sfh_predict_tail_args* args, void* stream);

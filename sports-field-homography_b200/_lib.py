@@ -53,7 +53,7 @@ class SfhPredictTailArgs(C.Structure):
                 ("nc", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("N", C.c_int32),
                 ("logits", C.c_void_p), ("warp_out", C.c_void_p), ("score", C.c_void_p),
                 ("court_poi", C.c_void_p), ("court_poi_bstride", C.c_int64), ("poi_out", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("mask_dtype", C.c_int32)]
 
 
 _P = C.c_void_p

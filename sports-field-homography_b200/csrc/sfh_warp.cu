@@ -54,7 +54,8 @@ struct FusedParams {
     // kEpiPredict
     const float* logits;
     int lh, lw, ratio;   // ratio: 1 (same size), 2 (H=2h, W=2w), 0 (score not fused)
-    int32_t* out_i;
+    int32_t* out_i;          // int32 mask (reference dtype) ...
+    unsigned char* out_u8;   // ... or uint8 mask (narrow surface, what predict.py:99 converts to anyway)
     float* score;
     // POI work, done by the first warp of tile 0 of every sample
     PoiParams poi;
@@ -478,7 +479,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             }
             if (EPI == kEpiPredict) {
                 const int ci = __float2int_rz(__fmul_rn(cval, ncf));
-                if (vec) __stcs((int4*)(p.out_i + rowbase), make_int4(ci, ci, ci, ci));
+                if (p.out_u8) {
+                    if (vec) __stcs((uchar4*)(p.out_u8 + rowbase), make_uchar4(ci, ci, ci, ci));
+                    else
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_u8[rowbase + j] = (unsigned char)ci;
+                } else if (vec) __stcs((int4*)(p.out_i + rowbase), make_int4(ci, ci, ci, ci));
                 else
 #pragma unroll
                     for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_i[rowbase + j] = ci;
@@ -616,7 +622,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                 else o = bilerp(px[j], taps.fetch4(0, px[j].x0, px[j].y0));
                 ci[j] = __float2int_rz(__fmul_rn(o, ncf));   // (warp*nc).int()
             }
-            if (vec) __stcs((int4*)(p.out_i + rowbase), make_int4(ci[0], ci[1], ci[2], ci[3]));
+            if (p.out_u8) {
+                if (vec) __stcs((uchar4*)(p.out_u8 + rowbase), make_uchar4(ci[0], ci[1], ci[2], ci[3]));
+                else
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_u8[rowbase + j] = (unsigned char)ci[j];
+            } else if (vec) __stcs((int4*)(p.out_i + rowbase), make_int4(ci[0], ci[1], ci[2], ci[3]));
             else
 #pragma unroll
                 for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_i[rowbase + j] = ci[j];
@@ -1126,7 +1137,7 @@ __global__ void __launch_bounds__(kThreads) k_train_finalize(const __grid_consta
 
 // Consistency score for logits sizes the fused pass does not cover (any h,w): reads the int32
 // mask back (L2-hot) with upsample_nearest's index rule.  models/reconstructor.py:230-238.
-__global__ void __launch_bounds__(kThreads) k_consistency_generic(const int32_t* mask, const float* logits,
+__global__ void __launch_bounds__(kThreads) k_consistency_generic(const int32_t* mask, const unsigned char* mask8, const float* logits,
                                                                   int nc, int H, int W, int lh, int lw,
                                                                   float* score) {
     __shared__ double s_w[kWarps];
@@ -1138,7 +1149,7 @@ __global__ void __launch_bounds__(kThreads) k_consistency_generic(const int32_t*
         const int r = (int)(i / lw), c = (int)(i % lw);
         int sr = (lh == H) ? r : (lh == 2 * H) ? (r >> 1) : min((int)floorf(r * sy), H - 1);
         int sc = (lw == W) ? c : (lw == 2 * W) ? (c >> 1) : min((int)floorf(c * sx), W - 1);
-        const int cls = mask[((size_t)b * H + sr) * W + sc];
+        const int cls = mask8 ? (int)mask8[((size_t)b * H + sr) * W + sc] : mask[((size_t)b * H + sr) * W + sc];
         acc += (double)ce_pixel(logits + (size_t)b * nc * cs + i, cs, nc, cls);
     }
     acc = warp_sum(acc);
@@ -1536,8 +1547,10 @@ int sfh_predict_tail(const sfh_template* tmpl, const sfh_predict_tail_args* a, v
     if (a->score && (!a->logits || a->h <= 0 || a->w <= 0)) return SFH_E_BADARG;
     FusedParams p;
     fill_common(p, a->theta, tmpl, a->xs, a->ys, a->B, a->H, a->W);
-    p.nc = a->nc; p.out_i = a->warp_out;
-    p.vec4 = (a->W % 4 == 0) && aligned16(a->warp_out);
+    p.nc = a->nc;
+    if (a->mask_dtype == SFH_MASK_U8) p.out_u8 = (unsigned char*)a->warp_out; else p.out_i = (int32_t*)a->warp_out;
+    if (a->mask_dtype != SFH_MASK_I32 && a->mask_dtype != SFH_MASK_U8) return SFH_E_BADARG;
+    p.vec4 = (a->W % 4 == 0) && (p.out_u8 ? (((uintptr_t)a->warp_out & 3u) == 0) : aligned16(a->warp_out));
     if (a->score) {
         if ((rc = setup_ws(p, a->workspace, a->workspace_bytes))) return rc;
         p.logits = a->logits; p.lh = a->h; p.lw = a->w; p.score = a->score;
@@ -1556,7 +1569,7 @@ int sfh_predict_tail(const sfh_template* tmpl, const sfh_predict_tail_args* a, v
     else return SFH_E_BADMODE;
     if (rc) return rc;
     if (a->score && p.ratio == 0) {
-        k_consistency_generic<<<a->B, kThreads, 0, st>>>(a->warp_out, a->logits, a->nc, a->H, a->W, a->h, a->w, a->score);
+        k_consistency_generic<<<a->B, kThreads, 0, st>>>(p.out_i, p.out_u8, a->logits, a->nc, a->H, a->W, a->h, a->w, a->score);
         rc = (int)cudaGetLastError();
     }
     return rc;

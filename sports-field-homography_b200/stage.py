@@ -237,9 +237,14 @@ class STNWarpStage(torch.nn.Module):
 
     @torch.no_grad()
     def predict_tail(self, theta: torch.Tensor, logits: Optional[torch.Tensor] = None,
-                     consistency: bool = True, project_poi: bool = False, out: Optional[dict] = None) -> dict:
+                     consistency: bool = True, project_poi: bool = False, out: Optional[dict] = None,
+                     mask_dtype: torch.dtype = torch.int32) -> dict:
         """Warp-stage part of Reconstructor.predict (models/reconstructor.py:221-245):
-        int32 warp_mask (= warp*mask_classes), consist_score [B], optional poi — one launch."""
+        int32 warp_mask (= warp*mask_classes), consist_score [B], optional poi — one launch.
+        ``mask_dtype=torch.uint8`` (opt-in) writes the mask as uint8, the dtype predict.py:99 converts
+        it to before it leaves the GPU worker."""
+        if mask_dtype not in (torch.int32, torch.uint8):
+            raise TypeError("mask_dtype must be torch.int32 or torch.uint8")
         theta9 = check_theta(theta, self.device)
         B, H, W = theta9.shape[0], self.height, self.width
         ret = {"theta": theta}
@@ -254,13 +259,14 @@ class STNWarpStage(torch.nn.Module):
         want_poi = project_poi and self.court_poi is not None
         N = self.court_poi.shape[1] if want_poi else 0
         poi = self._buf(out, "poi", (B, N, 2), torch.float32) if want_poi else None
-        mask = self._buf(out, "warp_mask", (B, H, W), torch.int32)
+        mask = self._buf(out, "warp_mask", (B, H, W), mask_dtype)
         xs, ys = self.warper.grid_factors(self.device)
         ws = _WS.get(self.device, B, H, W)
         a = _lib.SfhPredictTailArgs()
         a.theta, a.xs, a.ys = theta9.data_ptr(), xs.data_ptr(), ys.data_ptr()
         a.B, a.H, a.W, a.mode, a.nc, a.h, a.w, a.N = B, H, W, _lib.MODE[self.mode], self.mask_classes, h, w, N
         a.warp_out = mask.data_ptr()
+        a.mask_dtype = 1 if mask_dtype == torch.uint8 else 0
         if score is not None:
             a.logits, a.score = logits.data_ptr(), score.data_ptr()
         if want_poi:

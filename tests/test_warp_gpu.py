@@ -335,6 +335,10 @@ def test_predict_tail_matches_oracle(W, H, B, name):
     np.testing.assert_allclose(r["consist_score"].cpu().numpy(), s_ref, rtol=1e-5)
     p64 = co.poi_fwd(th.numpy(), poi.expand(B, -1, -1).numpy())
     assert np.abs(r["poi"].cpu().numpy() - p64).max() * W <= TOL_POI_PX
+    # uint8 mask at the surface (what predict.py:99 converts to): same classes, same score
+    r8 = st.predict_tail(th.to(DEV), logits.to(DEV), consistency=True, project_poi=False, mask_dtype=torch.uint8)
+    assert r8["warp_mask"].dtype == torch.uint8 and torch.equal(r8["warp_mask"].to(torch.int32), r["warp_mask"])
+    assert torch.equal(r8["consist_score"], r["consist_score"])
     # without consistency / poi the dict shrinks exactly like the reference's
     r2 = st.predict_tail(th.to(DEV), None, consistency=False, project_poi=False)
     assert set(r2) == {"theta", "warp_mask"} and torch.equal(r2["warp_mask"], r["warp_mask"])

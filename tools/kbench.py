@@ -70,6 +70,7 @@ for (W, H, B) in cfgs:
         run(f"train_u8gt_{W}x{H}_B{B}", lambda i: stb.train_step(S(i)["th"], S(i)["gt8"], S(i)["w"], "MSE", S(i)["gt_poi"], S(i)["nz"], S(i)["num"], 1.0, 8.0, True, S(i)["out"]), px * 5)
         run(f"train_nomask_{W}x{H}_B{B}", lambda i: stb.train_step(S(i)["th"], S(i)["gt"], S(i)["w"], "MSE", S(i)["gt_poi"], S(i)["nz"], S(i)["num"], 1.0, 8.0, False, S(i)["out"]), px * 8)
         run(f"predict_{W}x{H}_B{B}", lambda i: stn.predict_tail(S(i)["th"], S(i)["logits"], True, True, S(i)["outp"]), px * 4 + B * 4 * 360 * 640 * 4)
+        run(f"predict_u8mask_{W}x{H}_B{B}", lambda i: stn.predict_tail(S(i)["th"], S(i)["logits"], True, True, S(i).setdefault("outp8", {}), torch.uint8), px * 1 + B * 4 * 360 * 640 * 4)
         run(f"predict_noscore_{W}x{H}_B{B}", lambda i: stn.predict_tail(S(i)["th"], None, False, False, S(i)["outp"]), px * 4)
         go = torch.randn(B, 1, H, W, device=dev)
         thg = S(0)["th"]
