@@ -211,6 +211,11 @@ int sfh_reproj_loss(const float* inputs, const float* targets, const float* nonz
  * falls back to rcp.rn outside).  *mismatches (device uint64, pre-zeroed) receives the count. */
 int sfh_selftest_rcp(unsigned long long* mismatches, void* stream);
 
+/* Diagnostic: plain streaming kernel out[i] = (float)in[i] / 4 over n (multiple of 4) int64 -> fp32
+ * elements with `ctas` CTAs of 256 threads; moves the bytes of a training step with no other work
+ * (tools/stream_ceiling.py uses it to measure the size-matched streaming ceiling). */
+int sfh_debug_stream_cast(const int64_t* in, float* out, int64_t n, int ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

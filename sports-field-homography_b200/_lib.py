@@ -78,6 +78,7 @@ SIGNATURES = {
     "sfh_transform_points_bwd": (_I, [_P, _I, _P, _P, _I, _I, _P, _P, _P]),
     "sfh_reproj_loss": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "sfh_selftest_rcp": (_I, [_P, _P]),
+    "sfh_debug_stream_cast": (_I, [_P, _P, _L, _I, _P]),
 }
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

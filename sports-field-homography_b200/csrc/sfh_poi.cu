@@ -110,6 +110,17 @@ __global__ void k_selftest_rcp(unsigned long long* mismatches) {
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// Diagnostic streaming kernel: out[i] = (float)(int)in[i] * 0.25f over n int64 -> fp32, 4 elements
+// per thread per iteration (2 x 128-bit loads, 1 x 128-bit store), grid-stride.  Moves exactly the
+// bytes of one C2 step with no other work: the practical ceiling for a kernel of that size.
+__global__ void __launch_bounds__(256) k_stream_cast(const longlong2* __restrict__ in, float4* __restrict__ out, long long n4) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const longlong2 a = __ldcs(in + 2 * i), b = __ldcs(in + 2 * i + 1);
+        __stcs(out + i, make_float4((float)(int)a.x * 0.25f, (float)(int)a.y * 0.25f, (float)(int)b.x * 0.25f, (float)(int)b.y * 0.25f));
+    }
+}
+
 }  // namespace sfh
 
 using namespace sfh;
@@ -158,6 +169,12 @@ int sfh_reproj_loss(const float* inputs, const float* targets, const float* nonz
     if (!inputs || !targets || !nonzeros || !num_nonzero || B <= 0 || N <= 0) return SFH_E_BADARG;
     if (dinputs && !grad_Rb) return SFH_E_BADARG;
     k_reproj<<<B, 32, 0, (cudaStream_t)stream>>>(inputs, targets, nonzeros, num_nonzero, N, R_b, grad_Rb, dinputs);
+    return (int)cudaGetLastError();
+}
+
+int sfh_debug_stream_cast(const int64_t* in, float* out, int64_t n, int ctas, void* stream) {
+    if (!in || !out || n <= 0 || (n & 3) || ctas <= 0) return SFH_E_BADARG;
+    k_stream_cast<<<ctas, 256, 0, (cudaStream_t)stream>>>((const longlong2*)in, (float4*)out, n / 4);
     return (int)cudaGetLastError();
 }
 

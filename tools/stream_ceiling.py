@@ -2,8 +2,14 @@
 """Size-matched streaming ceilings on this GPU (development aid): what a plain fill / copy / cast
 kernel of the SAME byte volume as one bench step achieves, timed like tools/kbench.py.  Short
 kernels pay a fixed launch / ramp / drain cost that the 4 GB copy behind MEASURED_PEAKS.json does not."""
+import os
 import statistics
+import sys
+
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sfh_b200  # noqa: E402
 
 dev = torch.device("cuda:0")
 
@@ -37,5 +43,10 @@ for (W, H, B) in [(640, 360, 64), (1280, 720, 32)]:
     print(f"{W}x{H} B{B} copy fp32->fp32 ({n*8/1e6:.0f} MB r+w)       {us:7.1f} us {n*8/us/1e3:6.0f} GB/s")
     us = t(lambda: outs[nxt()].copy_(gts[i[0]]))
     print(f"{W}x{H} B{B} cast int64->fp32 ({n*12/1e6:.0f} MB r+w) = C2 bytes {us:7.1f} us {n*12/us/1e3:6.0f} GB/s")
+    lib = sfh_b200._lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    for ctas in (148 * 2, 148 * 4, 148 * 8, 148 * 16, 148 * 32):
+        us = t(lambda: lib.sfh_debug_stream_cast(gts[nxt()].data_ptr(), outs[i[0]].data_ptr(), n, ctas, st))
+        print(f"{W}x{H} B{B} own int64->fp32 stream kernel, {ctas:5d} CTAs ({n*12/1e6:.0f} MB)   {us:7.1f} us {n*12/us/1e3:6.0f} GB/s")
     us = t(lambda: gts[nxt()].sum())
     print(f"{W}x{H} B{B} sum int64 ({n*8/1e6:.0f} MB read)           {us:7.1f} us {n*8/us/1e3:6.0f} GB/s")
