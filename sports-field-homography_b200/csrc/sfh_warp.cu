@@ -778,10 +778,19 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 // sample's slots in fixed order in fp64 (results do not depend on which SM ran which chunk) and
 // applies the optional weighting / batch mean / total dtheta.
 // ------------------------------------------------------------------------------------------
-constexpr int kPCons = 15;                       // consumer warps
+#ifndef SFH_PCONS
+#define SFH_PCONS 15
+#endif
+#ifndef SFH_PSTAGES
+#define SFH_PSTAGES 4
+#endif
+#ifndef SFH_PR
+#define SFH_PR 4
+#endif
+constexpr int kPCons = SFH_PCONS;                // consumer warps
 constexpr int kPThreads = 32 * (kPCons + 1);     // 512: 4 warps per SM sub-partition
-constexpr int kPStages = 4;
-constexpr int kPR = 4;                           // bands per tile: 128 x 32 px
+constexpr int kPStages = SFH_PSTAGES;
+constexpr int kPR = SFH_PR;                      // bands per tile: 128 x 8*kPR px
 constexpr int kPItems = kPR * kWarps;            // 32 patches per tile
 constexpr int kPTileBytes = kPR * 8 * kTileW * 8;
 constexpr int kPChunk = 6;                       // tiles per chunk (consecutive tiles of one sample)
@@ -809,6 +818,7 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 // persistent kernel's producer then fills a pipeline stage with two bulk-async copies only.
 template <int FMT>
 __global__ void __launch_bounds__(kThreads) k_classify(const __grid_constant__ FusedParams p) {
+    constexpr int kGroups = (kPItems + 31) / 32;             // patches per lane
     const int H = p.H, W = p.W;
     const int lane = threadIdx.x & 31;
     const int tiles_x = (W + kTileW - 1) / kTileW;
@@ -820,53 +830,70 @@ __global__ void __launch_bounds__(kThreads) k_classify(const __grid_constant__ F
     const int band0 = ty * (8 * kPR);
     const int nitems = min(kPR, (H - band0 + 7) >> 3) * kWarps;
     const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
-    int cls = -1;
-    if ((FMT != SFH_TMPL_F32) && p.t.sat != nullptr && lane < nitems) {
-        Homog Hm;
-        Hm.load(p.theta + 9 * b);
-        const int r = lane / kWarps, k = lane % kWarps;
-        float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
-        bool zpos = true, zneg = true, fin = true;
+    int cls[kGroups];
+    unsigned bal[kGroups];
+    Homog Hm;
+    Hm.load(p.theta + 9 * b);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int grow = min(band0 + 8 * (r + (c >> 1)), H - 1);
-            const int gcol = min(tx * kTileW + kPatchW * (k + (c & 1)), W - 1);
-            const float gu = p.xs ? __ldg(p.xs + gcol) : mesh_coord(gcol, W);
-            const float gv = p.ys ? __ldg(p.ys + grow) : mesh_coord(grow, H);
-            const Flow f = flow_at(Hm, __fmul_rn(gu, Hm.h[0]), __fmul_rn(gu, Hm.h[3]), __fmul_rn(gu, Hm.h[6]), gv);
-            const float gx = __fmul_rn(__fmaf_rn(__fadd_rn(f.x, 1.0f), Wc_f, -1.0f), 0.5f);
-            const float gy = __fmul_rn(__fmaf_rn(__fadd_rn(f.y, 1.0f), Hc_f, -1.0f), 0.5f);
-            xmin = fminf(xmin, gx); xmax = fmaxf(xmax, gx);
-            ymin = fminf(ymin, gy); ymax = fmaxf(ymax, gy);
-            fin &= (gx == gx) & (gy == gy);
-            zpos &= f.zok & (f.s > 0.f);
-            zneg &= f.zok & (f.s < 0.f);
+    for (int h = 0; h < kGroups; ++h) {
+        const int id = lane + 32 * h;
+        cls[h] = -1;
+        if ((FMT != SFH_TMPL_F32) && p.t.sat != nullptr && id < nitems) {
+            const int r = id / kWarps, k = id % kWarps;
+            float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+            bool zpos = true, zneg = true, fin = true;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int grow = min(band0 + 8 * (r + (c >> 1)), H - 1);
+                const int gcol = min(tx * kTileW + kPatchW * (k + (c & 1)), W - 1);
+                const float gu = p.xs ? __ldg(p.xs + gcol) : mesh_coord(gcol, W);
+                const float gv = p.ys ? __ldg(p.ys + grow) : mesh_coord(grow, H);
+                const Flow f = flow_at(Hm, __fmul_rn(gu, Hm.h[0]), __fmul_rn(gu, Hm.h[3]), __fmul_rn(gu, Hm.h[6]), gv);
+                const float gx = __fmul_rn(__fmaf_rn(__fadd_rn(f.x, 1.0f), Wc_f, -1.0f), 0.5f);
+                const float gy = __fmul_rn(__fmaf_rn(__fadd_rn(f.y, 1.0f), Hc_f, -1.0f), 0.5f);
+                xmin = fminf(xmin, gx); xmax = fmaxf(xmax, gx);
+                ymin = fminf(ymin, gy); ymax = fmaxf(ymax, gy);
+                fin &= (gx == gx) & (gy == gy);
+                zpos &= f.zok & (f.s > 0.f);
+                zneg &= f.zok & (f.s < 0.f);
+            }
+            fin &= (xmin > -1e9f) & (xmax < 1e9f) & (ymin > -1e9f) & (ymax < 1e9f);
+            if ((zpos | zneg) & fin) {
+                const int wmax = p.t.width + 1, hmax = p.t.height + 1;
+                const int i0 = min(max(__float2int_rd(xmin - kBoxMargin) + 1, 0), wmax);
+                const int i1 = min(max(__float2int_rd(xmax + kBoxMargin) + 2, 0), wmax);
+                const int j0 = min(max(__float2int_rd(ymin - kBoxMargin) + 1, 0), hmax);
+                const int j1 = min(max(__float2int_rd(ymax + kBoxMargin) + 2, 0), hmax);
+                const unsigned* S = p.t.sat;
+                const int sp = p.t.sat_pitch;
+                Taps<FMT> taps;
+                taps.init(p.t, 0, nullptr);
+                const unsigned ec = taps.entry_class(i0, j0);
+                const unsigned cnt = __ldg(S + (j1 + 1) * sp + (i1 + 1)) - __ldg(S + j0 * sp + (i1 + 1))
+                                   - __ldg(S + (j1 + 1) * sp + i0) + __ldg(S + j0 * sp + i0);
+                if (cnt == 0u) cls[h] = (int)ec;
+            }
         }
-        fin &= (xmin > -1e9f) & (xmax < 1e9f) & (ymin > -1e9f) & (ymax < 1e9f);
-        if ((zpos | zneg) & fin) {
-            const int wmax = p.t.width + 1, hmax = p.t.height + 1;
-            const int i0 = min(max(__float2int_rd(xmin - kBoxMargin) + 1, 0), wmax);
-            const int i1 = min(max(__float2int_rd(xmax + kBoxMargin) + 2, 0), wmax);
-            const int j0 = min(max(__float2int_rd(ymin - kBoxMargin) + 1, 0), hmax);
-            const int j1 = min(max(__float2int_rd(ymax + kBoxMargin) + 2, 0), hmax);
-            const unsigned* S = p.t.sat;
-            const int sp = p.t.sat_pitch;
-            Taps<FMT> taps;
-            taps.init(p.t, 0, nullptr);
-            const unsigned ec = taps.entry_class(i0, j0);
-            const unsigned cnt = __ldg(S + (j1 + 1) * sp + (i1 + 1)) - __ldg(S + j0 * sp + (i1 + 1))
-                               - __ldg(S + (j1 + 1) * sp + i0) + __ldg(S + j0 * sp + i0);
-            if (cnt == 0u) cls = (int)ec;
-        }
+        bal[h] = __ballot_sync(0xffffffffu, (id < nitems) && cls[h] < 0);
     }
-    const bool e = (lane < nitems) && cls < 0;
-    const unsigned bal = __ballot_sync(0xffffffffu, e);
+    int total = 0;
+#pragma unroll
+    for (int h = 0; h < kGroups; ++h) total += __popc(bal[h]);
     unsigned short* out = p.lists + (size_t)tile * kPItems;
-    if (lane < nitems) {
-        const int before = __popc(bal & ((1u << lane) - 1u)), total = __popc(bal);
-        out[e ? before : total + (lane - before)] = (unsigned short)(lane | ((cls + 1) << 8));
-    } else {
-        out[lane] = 0xffffu;
+    int before_groups = 0;
+#pragma unroll
+    for (int h = 0; h < kGroups; ++h) {
+        const int id = lane + 32 * h;
+        if (id < kPItems) {
+            if (id < nitems) {
+                const bool e = cls[h] < 0;
+                const int before = before_groups + __popc(bal[h] & ((1u << lane) - 1u));
+                out[e ? before : total + (id - before)] = (unsigned short)(id | ((cls[h] + 1) << 8));
+            } else {
+                out[id] = 0xffffu;
+            }
+        }
+        before_groups += __popc(bal[h]);
     }
 }
 
