@@ -32,6 +32,9 @@ struct FusedParams {
     int ntiles;          // CTAs per sample
     int vec4;            // W % 4 == 0 and all row bases 16-byte aligned
     int use_tma;         // the CTA's gt tile (loss) / logits tile (predict) is staged in smem by one TMA load
+    int split_finalize;  // kEpiLoss: CTAs only write their partials; k_train_finalize (next launch) reduces them
+    int fin_slots;       // partial slots per sample read by k_train_finalize
+    int short_last;      // H % (8R) != 0: the short bottom tiles of all samples are dispatched last (shorter tail)
     // kEpiStore / kEpiBwd
     float* out_f;        // [B,C,H,W]
     const float* grad_out;
@@ -62,7 +65,6 @@ struct FusedParams {
     // workspace
     int* counters;
     float* partials;
-    unsigned short* lists;   // persistent path: per 128x32 tile, 32 patch entries, edge patches first
 };
 
 // Geometry of one output pixel, everything the epilogues need.
@@ -288,12 +290,33 @@ __device__ __forceinline__ void tl_stamp(int cta, int phase) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         g_timeline[(size_t)cta * 8 + phase] = (long long)t;
+        if (phase == 0) {
+            unsigned sm;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            g_timeline[(size_t)cta * 8 + 7] = (long long)sm;
+        }
     }
 }
 #define SFH_TL(phase) tl_stamp((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, phase)
+// streaming kernel: stamps of the first 8 tiles of every CTA, taken by lane 0 of warp 1 (phases 0-4) and warp 0 (5-7)
+#define SFH_TLS(w, phase) do { if (g_timeline && i < 8 && warp == (w) && lane == 0) { unsigned long long t_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_timeline[((size_t)blockIdx.x * 8 + i) * 8 + (phase)] = (long long)t_; } } while (0)
 #else
 #define SFH_TL(phase)
+#define SFH_TLS(w, phase)
 #endif
+
+// (sample, tile row) of this CTA.  CTAs are dispatched x-fastest, then y, then z; with `short_last`
+// (z, y) is remapped so that every sample's full-height tile rows come first and the short bottom
+// rows of all samples form the end of the grid (a shorter tail).
+__device__ __forceinline__ void block_tile(int short_last, int& b, int& ty) {
+    b = blockIdx.z; ty = blockIdx.y;
+    if (short_last) {
+        const int full = (int)gridDim.y - 1, L = (int)(blockIdx.z * gridDim.y + blockIdx.y), nfull = full * (int)gridDim.z;
+        if (L < nfull) { b = L / full; ty = L - b * full; }
+        else { b = L - nfull; ty = full; }
+    }
+}
 
 template <int FMT, int MODE, int EPI, bool FT>
 __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_constant__ FusedParams p) {
@@ -310,7 +333,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     // the loss epilogue always samples bilinearly; its MODE argument carries the criterion instead
     constexpr int SMODE = (EPI == kEpiLoss) ? SFH_MODE_BILINEAR : MODE;
     constexpr bool kMse = (EPI != kEpiLoss) || (MODE == SFH_LOSS_MSE);
-    const int b = blockIdx.z, tx = blockIdx.x, ty = blockIdx.y;
+    int b, ty;
+    const int tx = blockIdx.x;
+    block_tile(p.short_last, b, ty);
     const int tile = ty * gridDim.x + tx;
     const int H = p.H, W = p.W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -322,6 +347,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     const bool tma = (EPI == kEpiLoss || EPI == kEpiPredict) && p.use_tma;
 
     SFH_TL(0);
+    if (EPI == kEpiLoss) asm volatile("griddepcontrol.launch_dependents;");   // lets k_train_finalize become resident early
     if (tma && threadIdx.x == 0) {
         // the tile's streaming input is requested before anything else so that it arrives behind
         // the whole prologue (evict-first in L2: it is read exactly once)
@@ -669,6 +695,14 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     SFH_TL(4);
 
     // ---------------- per-sample reduction: lane -> warp -> CTA partial -> last CTA -----------
+    // (sample, tile) are recomputed here so that they are not live across the patch loop
+    int bE, tyE;
+    {
+        int sl = p.short_last;
+        asm volatile("" : "+r"(sl));
+        block_tile(sl, bE, tyE);
+    }
+    const int tileE = tyE * gridDim.x + tx;
     if (EPI == kEpiLoss && !kMse) loss_sum *= 0.5f;
     {
         float vals[16];
@@ -686,11 +720,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) s += s_red[w][threadIdx.x];
-        __stcg(p.partials + ((size_t)b * p.ntiles + tile) * kNPart + threadIdx.x, s);
+        __stcg(p.partials + ((size_t)bE * p.ntiles + tileE) * kNPart + threadIdx.x, s);
     }
+    if (EPI == kEpiLoss && p.split_finalize) return;   // reduced by k_train_finalize
     __syncthreads();
     SFH_TL(5);
-    if (threadIdx.x == 0) s_last = (ticket_release(p.counters + b) == p.ntiles - 1);
+    if (threadIdx.x == 0) s_last = (ticket_release(p.counters + bE) == p.ntiles - 1);
     SFH_TL(6);
     __syncthreads();
     if (!s_last) return;
@@ -699,7 +734,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         const int k = threadIdx.x / kFinGroup, jj = threadIdx.x % kFinGroup;
         if (k < kNPart) {
             double s = 0.0;
-            const float* base = p.partials + (size_t)b * p.ntiles * kNPart + k;
+            const float* base = p.partials + (size_t)bE * p.ntiles * kNPart + k;
             for (int t = jj; t < p.ntiles; t += kFinGroup) s += (double)__ldcg(base + (size_t)t * kNPart);
             s_fin[k][jj] = s;
         }
@@ -711,13 +746,13 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 #pragma unroll
         for (int jj = 0; jj < kFinGroup; ++jj) s += s_fin[k][jj];
         if (EPI == kEpiBwd) {
-            if (k >= 1 && k <= 9) p.dtheta[9 * b + k - 1] = (float)s;
+            if (k >= 1 && k <= 9) p.dtheta[9 * bE + k - 1] = (float)s;
         } else if (EPI == kEpiLoss) {
-            if (k == 0) { s = s / ((double)H * (double)W); p.Lb[b] = (float)s; }
-            else if (k <= 9) p.J[9 * b + k - 1] = (float)s;
+            if (k == 0) { s = s / ((double)H * (double)W); p.Lb[bE] = (float)s; }
+            else if (k <= 9) p.J[9 * bE + k - 1] = (float)s;
             s_fin[k][0] = s;
         } else if (EPI == kEpiPredict) {
-            if (k == 10) p.score[b] = (float)(s / ((double)p.lh * (double)p.lw));
+            if (k == 10) p.score[bE] = (float)(s / ((double)p.lh * (double)p.lw));
         }
     }
     if (EPI == kEpiLoss && p.loss_out) {
@@ -733,23 +768,23 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                         sw += p.w_f64 ? ((const double*)p.weights)[i] : (double)((const float*)p.weights)[i];
                     w_eff = warp_sum(sw) / (double)B;
                 } else {
-                    w_eff = p.w_f64 ? ((const double*)p.weights)[b] : (double)((const float*)p.weights)[b];
+                    w_eff = p.w_f64 ? ((const double*)p.weights)[bE] : (double)((const float*)p.weights)[bE];
                 }
             }
             const bool rep = p.poi.gt_poi != nullptr;
             const double cr = (double)p.rec_lambda * w_eff, cp = (double)p.reproj_lambda;
             if (lane < 9) {
-                const double Kk = rep ? (double)__ldcg(p.poi.K + 9 * b + lane) : 0.0;
-                p.dtheta_total[9 * b + lane] = (float)((cr * s_fin[1 + lane][0] + cp * Kk) / (double)B);
+                const double Kk = rep ? (double)__ldcg(p.poi.K + 9 * bE + lane) : 0.0;
+                p.dtheta_total[9 * bE + lane] = (float)((cr * s_fin[1 + lane][0] + cp * Kk) / (double)B);
             }
             int last2 = 0;
             if (lane == 0) {
-                const double Rv = rep ? (double)__ldcg(p.poi.Rb + b) : 0.0;
-                __stcg(p.contrib + b, cr * s_fin[0][0] + cp * Rv);
+                const double Rv = rep ? (double)__ldcg(p.poi.Rb + bE) : 0.0;
+                __stcg(p.contrib + bE, cr * s_fin[0][0] + cp * Rv);
                 last2 = (ticket_release(p.counters + B) == B - 1);
             }
             last2 = __shfl_sync(0xffffffffu, last2, 0);
-            if (last2) {                    // last sample of the batch: fixed-order sum over b
+            if (last2) {                    // last sample of the batch: fixed-order sum over bE
                 __threadfence();
                 double s = 0.0;
                 for (int i = lane; i < B; i += 32) s += __ldcg(p.contrib + i);
@@ -758,246 +793,275 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             }
         }
     }
-    if (threadIdx.x == 0) p.counters[b] = 0;   // leave the workspace zeroed for the next call
+    if (threadIdx.x == 0) p.counters[bE] = 0;   // leave the workspace zeroed for the next call
 }
 
 // ------------------------------------------------------------------------------------------
-// Persistent, warp-specialised training kernel (kEpiLoss with TMA-staged gt tiles).
+// Streaming training kernel (kEpiLoss with TMA-staged gt tiles): k_fused's loss epilogue turned
+// into a persistent loop so that the per-CTA fixed costs (tables, barriers, launch gaps, the
+// ticket's MEMBAR) are paid once per CTA instead of once per tile, and a gt tile is always in
+// flight while the previous one is being consumed.
 //
-// One CTA per SM: 1 producer warp + 15 consumer warps, a 4-stage ring of 128 x 32 px tiles.
-//   producer   takes chunks of consecutive tiles of one sample from a global ticket; per tile it
-//              issues ONE TMA tensor load for the int64 gt tile (32 KiB) and, while that is in
-//              flight, loads theta, classifies the tile's 32 patches against the edge summed-area
-//              table and writes the edge-first patch list into the stage; it then arrives on the
-//              stage's `full` mbarrier (the TMA completes the tx count of the same barrier).
-//   consumers  wait on `full`, take patches of the list round-robin (per-pixel path for edge
-//              patches, constant path otherwise), arrive on the stage's `empty` mbarrier, and keep
-//              their 10 sums in registers for the whole chunk; at a chunk boundary a 16-value
-//              shuffle butterfly writes them to the fixed slot (sample, chunk, warp).
-// No __syncthreads, no atomics and no fences in the steady state.  k_train_finalize then adds every
-// sample's slots in fixed order in fp64 (results do not depend on which SM ran which chunk) and
-// applies the optional weighting / batch mean / total dtheta.
+//   * grid = resident CTAs only (3 per SM); CTA c walks tiles c, c+G, c+2G, ... (128 x 8*kLR px)
+//   * a kLS-stage ring of gt tiles in smem; lane 0 of warp 0 issues the TMA load of tile i+kLS-1
+//     once every warp has released the stage (`empty` mbarrier, 8 arrivals), all warps wait on
+//     the stage's `full` mbarrier.  No __syncthreads in the loop: warps run up to a stage apart.
+//   * every warp classifies the tile's <= 32 patches itself (one lane per patch; redundant across
+//     warps but sync-free); the summed-area-table loads of tile i+1 are issued before tile i is
+//     processed, so their latency is hidden behind the pixel work
+//   * per tile every warp writes its 10 sums to the fixed slot (tile, warp): results do not depend
+//     on which CTA ran which tile.  k_train_finalize then adds every sample's slots in fixed
+//     order in fp64 and applies the optional weighting / batch mean / total dtheta.
 // ------------------------------------------------------------------------------------------
-#ifndef SFH_PCONS
-#define SFH_PCONS 15
+#ifndef SFH_LR
+#define SFH_LR 4
 #endif
-#ifndef SFH_PSTAGES
-#define SFH_PSTAGES 4
+#ifndef SFH_LS
+#define SFH_LS 3
 #endif
-#ifndef SFH_PR
-#define SFH_PR 4
+#ifndef SFH_STREAM_CTAS
+#define SFH_STREAM_CTAS 2   // 128 registers: no spills; measured faster than 3 CTAs/SM at 80
 #endif
-constexpr int kPCons = SFH_PCONS;                // consumer warps
-constexpr int kPThreads = 32 * (kPCons + 1);     // 512: 4 warps per SM sub-partition
-constexpr int kPStages = SFH_PSTAGES;
-constexpr int kPR = SFH_PR;                      // bands per tile: 128 x 8*kPR px
-constexpr int kPItems = kPR * kWarps;            // 32 patches per tile
-constexpr int kPTileBytes = kPR * 8 * kTileW * 8;
-constexpr int kPChunk = 6;                       // tiles per chunk (consecutive tiles of one sample)
+constexpr int kLR = SFH_LR;                      // bands per tile: 128 x 8*kLR px
+constexpr int kLS = SFH_LS;                      // ring stages
+constexpr int kLItems = kLR * kWarps;            // patches per tile, one lane each
+static_assert(kLItems <= 32, "one lane per patch");
+constexpr int kLStageBytes = kLR * 8 * kTileW * 8;
+constexpr int kLMaxB = 1024;                     // theta table in smem: 36 B per sample
 
-struct __align__(16) PStage {
-    unsigned short items[kPItems];
-    float theta[9];
-    int b, tx, ty, nitems, slot;                 // nitems < 0: no more tiles; slot >= 0: last tile of its chunk
-};
-
-__device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
+// classification of one patch, split in two so the table loads can be in flight across a tile
+struct ClsPend {
+    unsigned ec, s11, s01, s10, s00;
+    bool box;                                    // the 4-corner bounding box is usable
+};
 
-// Patch classification for the persistent path: one warp per 128 x 32 tile, one lane per 16 x 8
-// patch.  Writes the tile's edge-first patch list (32 x uint16 = 64 B) to the workspace; the
-// persistent kernel's producer then fills a pipeline stage with two bulk-async copies only.
 template <int FMT>
-__global__ void __launch_bounds__(kThreads) k_classify(const __grid_constant__ FusedParams p) {
-    constexpr int kGroups = (kPItems + 31) / 32;             // patches per lane
+__device__ __forceinline__ ClsPend classify_issue(const FusedParams& p, const Taps<FMT>& taps, const float* th,
+                                                  int tx, int band0, int id, bool active) {
+    ClsPend c;
+    c.box = false;
+    c.ec = c.s11 = c.s01 = c.s10 = c.s00 = 0u;
+    if ((FMT == SFH_TMPL_F32) || p.t.sat == nullptr || !active) return c;
     const int H = p.H, W = p.W;
-    const int lane = threadIdx.x & 31;
-    const int tiles_x = (W + kTileW - 1) / kTileW;
-    const int tiles_per_sample = tiles_x * ((H + 8 * kPR - 1) / (8 * kPR));
-    const int tile = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    if (tile >= tiles_per_sample * p.B) return;
-    const int b = tile / tiles_per_sample, rem = tile - b * tiles_per_sample;
-    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-    const int band0 = ty * (8 * kPR);
-    const int nitems = min(kPR, (H - band0 + 7) >> 3) * kWarps;
     const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
-    int cls[kGroups];
-    unsigned bal[kGroups];
     Homog Hm;
-    Hm.load(p.theta + 9 * b);
 #pragma unroll
-    for (int h = 0; h < kGroups; ++h) {
-        const int id = lane + 32 * h;
-        cls[h] = -1;
-        if ((FMT != SFH_TMPL_F32) && p.t.sat != nullptr && id < nitems) {
-            const int r = id / kWarps, k = id % kWarps;
-            float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
-            bool zpos = true, zneg = true, fin = true;
+    for (int k = 0; k < 9; ++k) Hm.h[k] = th[k];
+    const int r = id / kWarps, k = id % kWarps;
+    float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+    bool zpos = true, zneg = true, fin = true;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int grow = min(band0 + 8 * (r + (c >> 1)), H - 1);
-                const int gcol = min(tx * kTileW + kPatchW * (k + (c & 1)), W - 1);
-                const float gu = p.xs ? __ldg(p.xs + gcol) : mesh_coord(gcol, W);
-                const float gv = p.ys ? __ldg(p.ys + grow) : mesh_coord(grow, H);
-                const Flow f = flow_at(Hm, __fmul_rn(gu, Hm.h[0]), __fmul_rn(gu, Hm.h[3]), __fmul_rn(gu, Hm.h[6]), gv);
-                const float gx = __fmul_rn(__fmaf_rn(__fadd_rn(f.x, 1.0f), Wc_f, -1.0f), 0.5f);
-                const float gy = __fmul_rn(__fmaf_rn(__fadd_rn(f.y, 1.0f), Hc_f, -1.0f), 0.5f);
-                xmin = fminf(xmin, gx); xmax = fmaxf(xmax, gx);
-                ymin = fminf(ymin, gy); ymax = fmaxf(ymax, gy);
-                fin &= (gx == gx) & (gy == gy);
-                zpos &= f.zok & (f.s > 0.f);
-                zneg &= f.zok & (f.s < 0.f);
-            }
-            fin &= (xmin > -1e9f) & (xmax < 1e9f) & (ymin > -1e9f) & (ymax < 1e9f);
-            if ((zpos | zneg) & fin) {
-                const int wmax = p.t.width + 1, hmax = p.t.height + 1;
-                const int i0 = min(max(__float2int_rd(xmin - kBoxMargin) + 1, 0), wmax);
-                const int i1 = min(max(__float2int_rd(xmax + kBoxMargin) + 2, 0), wmax);
-                const int j0 = min(max(__float2int_rd(ymin - kBoxMargin) + 1, 0), hmax);
-                const int j1 = min(max(__float2int_rd(ymax + kBoxMargin) + 2, 0), hmax);
-                const unsigned* S = p.t.sat;
-                const int sp = p.t.sat_pitch;
-                Taps<FMT> taps;
-                taps.init(p.t, 0, nullptr);
-                const unsigned ec = taps.entry_class(i0, j0);
-                const unsigned cnt = __ldg(S + (j1 + 1) * sp + (i1 + 1)) - __ldg(S + j0 * sp + (i1 + 1))
-                                   - __ldg(S + (j1 + 1) * sp + i0) + __ldg(S + j0 * sp + i0);
-                if (cnt == 0u) cls[h] = (int)ec;
-            }
-        }
-        bal[h] = __ballot_sync(0xffffffffu, (id < nitems) && cls[h] < 0);
+    for (int q = 0; q < 4; ++q) {
+        const int grow = min(band0 + 8 * (r + (q >> 1)), H - 1);
+        const int gcol = min(tx * kTileW + kPatchW * (k + (q & 1)), W - 1);
+        const float gu = p.xs ? __ldg(p.xs + gcol) : mesh_coord(gcol, W);
+        const float gv = p.ys ? __ldg(p.ys + grow) : mesh_coord(grow, H);
+        const Flow f = flow_at(Hm, __fmul_rn(gu, Hm.h[0]), __fmul_rn(gu, Hm.h[3]), __fmul_rn(gu, Hm.h[6]), gv);
+        const float gx = __fmul_rn(__fmaf_rn(__fadd_rn(f.x, 1.0f), Wc_f, -1.0f), 0.5f);
+        const float gy = __fmul_rn(__fmaf_rn(__fadd_rn(f.y, 1.0f), Hc_f, -1.0f), 0.5f);
+        xmin = fminf(xmin, gx); xmax = fmaxf(xmax, gx);
+        ymin = fminf(ymin, gy); ymax = fmaxf(ymax, gy);
+        fin &= (gx == gx) & (gy == gy);
+        zpos &= f.zok & (f.s > 0.f);          // Z of one sign at the 4 corners => no horizon inside
+        zneg &= f.zok & (f.s < 0.f);
     }
-    int total = 0;
-#pragma unroll
-    for (int h = 0; h < kGroups; ++h) total += __popc(bal[h]);
-    unsigned short* out = p.lists + (size_t)tile * kPItems;
-    int before_groups = 0;
-#pragma unroll
-    for (int h = 0; h < kGroups; ++h) {
-        const int id = lane + 32 * h;
-        if (id < kPItems) {
-            if (id < nitems) {
-                const bool e = cls[h] < 0;
-                const int before = before_groups + __popc(bal[h] & ((1u << lane) - 1u));
-                out[e ? before : total + (id - before)] = (unsigned short)(id | ((cls[h] + 1) << 8));
-            } else {
-                out[id] = 0xffffu;
-            }
-        }
-        before_groups += __popc(bal[h]);
+    fin &= (xmin > -1e9f) & (xmax < 1e9f) & (ymin > -1e9f) & (ymax < 1e9f);
+    if ((zpos | zneg) & fin) {
+        const int wmax = p.t.width + 1, hmax = p.t.height + 1;
+        const int i0 = min(max(__float2int_rd(xmin - kBoxMargin) + 1, 0), wmax);
+        const int i1 = min(max(__float2int_rd(xmax + kBoxMargin) + 2, 0), wmax);
+        const int j0 = min(max(__float2int_rd(ymin - kBoxMargin) + 1, 0), hmax);
+        const int j1 = min(max(__float2int_rd(ymax + kBoxMargin) + 2, 0), hmax);
+        const unsigned* S = p.t.sat;
+        const int sp = p.t.sat_pitch;
+        c.box = true;
+        c.ec = taps.entry_class(i0, j0);
+        c.s11 = __ldg(S + (j1 + 1) * sp + (i1 + 1));
+        c.s01 = __ldg(S + j0 * sp + (i1 + 1));
+        c.s10 = __ldg(S + (j1 + 1) * sp + i0);
+        c.s00 = __ldg(S + j0 * sp + i0);
     }
+    return c;
+}
+__device__ __forceinline__ int classify_finish(const ClsPend& c) {      // class of an edge-free patch, else -1
+    return (c.box && (c.s11 - c.s01 - c.s10 + c.s00) == 0u) ? (int)c.ec : -1;
 }
 
-template <int FMT, bool FT>
-__global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_constant__ FusedParams p) {
-    extern __shared__ __align__(128) unsigned char s_dyn[];            // kPStages gt tiles (TMA destinations)
+constexpr int kLLook = kWarps;                   // tile i's patch list is built by warp i % 8 while it works on tile i - 8
+constexpr int kLSlots = 2 * kLLook;              // list ring
+constexpr int kLStash = (kLItems + kWarps - 2) / (kWarps - 1);   // edge patches one of warps 1..7 can get from a tile
+
+template <int FMT, bool FT, bool KMSE>
+__global__ void __launch_bounds__(kThreads, SFH_STREAM_CTAS) k_train_stream(const __grid_constant__ FusedParams p) {
+    extern __shared__ __align__(128) unsigned char s_dyn[];            // kLS gt stages, then theta [B][9]
     __shared__ __align__(16) float s_tab[Taps<FMT>::kSmemFloats];
-    __shared__ __align__(16) PStage s_stage[kPStages];
-    __shared__ __align__(8) uint64_t s_full[kPStages], s_empty[kPStages];
+    __shared__ unsigned short s_list[kLSlots][32];                     // ring of per-tile patch lists
+    __shared__ int s_lcount[kLSlots];                                  // ... and their number of edge entries
+    __shared__ __align__(8) uint64_t s_full[kLS], s_empty[kLS], s_lfull[kLSlots];
 
     const int H = p.H, W = p.W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = lane & 3, ly = lane >> 2;
     const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
     const int tiles_x = (W + kTileW - 1) / kTileW;
-    const int tiles_per_sample = tiles_x * ((H + 8 * kPR - 1) / (8 * kPR));
-    const int chunks_per_sample = (tiles_per_sample + kPChunk - 1) / kPChunk;
-    const int total_chunks = chunks_per_sample * p.B;
-    int* chunk_ctr = p.counters + p.B + 1;
+    const int tps = p.ntiles;                                          // tiles per sample
+    const int tiles_y = tps / tiles_x;
+    const int total = tps * p.B;
+    const int G = (int)gridDim.x;
+    const int n = (total - (int)blockIdx.x + G - 1) / G;               // tiles of this CTA: blockIdx.x + i*G
+    const uint32_t tile_bytes = (uint32_t)(kLR * 8 * kTileW) * (p.gt8 ? 1u : 8u);
+    float* s_theta = reinterpret_cast<float*>(s_dyn + kLS * kLStageBytes);
+    const uint64_t pol = l2_policy_evict_first();
 
-    Taps<FMT> taps;
-    if (threadIdx.x < kThreads) taps.build_tables(p.t, s_tab);         // 256-entry LUT: first 256 threads
+    auto tile_coords = [&](int i, int& b, int& tx, int& ty) {          // divisions: used off the per-tile path only
+        const int t = (int)blockIdx.x + i * G;
+        b = t / tps;
+        const int rem = t - b * tps;
+        ty = rem / tiles_x;
+        tx = rem - ty * tiles_x;
+    };
+    auto issue_tile = [&](int j) {                                     // one thread
+        int b, tx, ty;
+        tile_coords(j, b, tx, ty);
+        const int sj = j % kLS;
+        mbar_expect_tx(&s_full[sj], tile_bytes);
+        tma_load_3d(s_dyn + (size_t)sj * kLStageBytes, &p.gt_map, tx * kTileW, ty * (8 * kLR), b, &s_full[sj], pol);
+    };
+    // the patch list of tile j: classify (table loads in flight) ... finish (ballot, edge patches first)
+    auto list_issue = [&](int j, const Taps<FMT>& taps, int& nitems) {
+        int b, tx, ty;
+        tile_coords(j, b, tx, ty);
+        nitems = min(kLR, (H - ty * (8 * kLR) + 7) >> 3) * kWarps;
+        return classify_issue<FMT>(p, taps, s_theta + 9 * b, tx, ty * (8 * kLR), lane, lane < nitems);
+    };
+    auto list_finish = [&](int j, const ClsPend& pend, int nitems) {
+        const int cls = classify_finish(pend);
+        const bool is_edge = (lane < nitems) && cls < 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, is_edge);
+        const int before = __popc(bal & ((1u << lane) - 1u));
+        unsigned short* l = s_list[j % kLSlots];
+        if (lane < nitems) l[is_edge ? before : __popc(bal) + (lane - before)] = (unsigned short)(lane | ((cls + 1) << 8));
+        if (lane == 0) s_lcount[j % kLSlots] = __popc(bal);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_lfull[j % kLSlots]);             // release: the list is visible to its waiters
+    };
+
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < kPStages; ++s) {
+        for (int s = 0; s < kLS; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_full[s])), "r"(1) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_empty[s])), "r"(kPCons) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_empty[s])), "r"(kWarps) : "memory");
         }
+#pragma unroll
+        for (int s = 0; s < kLSlots; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_lfull[s])), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int j = 0; j < kLS - 1 && j < n; ++j) issue_tile(j);      // streams in behind the prologue
     }
+    Taps<FMT> taps;
+    taps.build_tables(p.t, s_tab);
+    for (int i = threadIdx.x; i < 9 * p.B; i += kThreads) s_theta[i] = __ldg(p.theta + i);
     __syncthreads();
     taps.init(p.t, 0, s_tab);
-
-    if (warp == kPCons) {
-        // ============ producer warp: two bulk-async copies per tile, nothing else ============
-        int it = 0;
-        int chunk = 0;
-        if (lane == 0) chunk = atomicAdd(chunk_ctr, 1);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        while (chunk < total_chunks) {
-            int next_chunk = 0;
-            if (lane == 0) next_chunk = atomicAdd(chunk_ctr, 1);        // prefetched; consumed after this chunk
-            const int b = chunk / chunks_per_sample, cis = chunk - b * chunks_per_sample;
-            const int t0 = cis * kPChunk, t1 = min(t0 + kPChunk, tiles_per_sample);
-            const float th = (lane < 9) ? __ldg(p.theta + 9 * b + lane) : 0.f;
-            if (cis == 0 && p.poi.court_poi) poi_warp(p.poi, b, lane);  // the sample's court points (fp64)
-            for (int rem = t0; rem < t1; ++rem, ++it) {
-                const int s = it % kPStages;
-                mbar_wait(&s_empty[s], ((it / kPStages) & 1) ^ 1);      // consumers released this stage
-                PStage& st = s_stage[s];
-                const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-                const int band0 = ty * (8 * kPR);
-                if (lane == 0) {
-                    mbar_expect_tx_only(&s_full[s], (uint32_t)(kPTileBytes + kPItems * 2));
-                    tma_load_3d(s_dyn + (size_t)s * kPTileBytes, &p.gt_map, tx * kTileW, band0, b, &s_full[s]);
-                    bulk_load(st.items, p.lists + ((size_t)b * tiles_per_sample + rem) * kPItems, kPItems * 2, &s_full[s]);
-                    st.b = b; st.tx = tx; st.ty = ty;
-                    st.nitems = min(kPR, (H - band0 + 7) >> 3) * kWarps;
-                    st.slot = (rem == t1 - 1) ? (b * chunks_per_sample + cis) : -1;
-                }
-                if (lane < 9) st.theta[lane] = th;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_full[s]);                 // + the copies' tx bytes => phase completes
-            }
-            chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
-        }
-        // no more work: poison the next stage so the consumers leave
-        const int s = it % kPStages;
-        mbar_wait(&s_empty[s], ((it / kPStages) & 1) ^ 1);
-        if (lane == 0) { s_stage[s].nitems = -1; }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_full[s]);
-        return;
+    if (warp < n) {                                                    // lists of the first 8 tiles: one per warp
+        int nit;
+        const ClsPend pend = list_issue(warp, taps, nit);
+        list_finish(warp, pend, nit);
     }
 
-    // ===================================== consumer warps =====================================
-    const int cw = warp;
-    const int lx = lane & 3, ly = lane >> 2;
-    const int lane_px = ly * kTileW + lx * 4;                           // lane's offset inside a patch row block
     const float halfWc = 0.5f * Wc_f, halfHc = 0.5f * Hc_f;
-    const float gscale = (p.kind == SFH_LOSS_MSE ? 2.0f : 1.0f) * p.invN;
+    const float gscale = (KMSE ? 2.0f : 1.0f) * p.invN;
     const float ncf = (float)p.nc;
     GradAcc acc;
     acc.zero();
     float loss_sum = 0.f;
-    for (int it = 0;; ++it) {
-        const int s = it % kPStages;
-        mbar_wait(&s_full[s], (it / kPStages) & 1);
-        const PStage& st = s_stage[s];
-        const int nitems = st.nitems;
-        if (nitems < 0) break;
-        const int b = st.b, tx = st.tx, band0 = st.ty * (8 * kPR), slot = st.slot;
-        const long long* s_gt = reinterpret_cast<const long long*>(s_dyn + (size_t)s * kPTileBytes);
-        const size_t base_b = (size_t)b * H * W;
-        float* outb = p.out_f ? p.out_f + base_b : nullptr;
+    int erot = 0;                                                      // edge patches dealt so far, mod 7
+
+    // tile walk without divisions: G = dB * tps + dY * tiles_x + dX
+    const int dB = G / tps, dY = (G - dB * tps) / tiles_x, dX = G - dB * tps - dY * tiles_x;
+    int b, tx, ty;
+    tile_coords(0, b, tx, ty);
+    int t = (int)blockIdx.x;
+
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        const int band0 = ty * (8 * kLR);
+        const int nitems = min(kLR, (H - band0 + 7) >> 3) * kWarps;
+        const int s = i % kLS;
+
+        SFH_TLS(1, 0); SFH_TLS(0, 5);
+        // producer duty: refill the stage tile i-1 has just left
+        if (warp == 0) {
+            const int j = i + kLS - 1;
+            if (j < n && lane == 0) {
+                mbar_wait(&s_empty[j % kLS], ((j / kLS) & 1) ^ 1);
+                issue_tile(j);
+            }
+            __syncwarp();
+        }
+        if (warp == kWarps - 1 && t == b * tps && p.poi.court_poi) poi_warp(p.poi, b, lane);   // the sample's court points (fp64)
+
+        // list duty: this warp builds the list of tile i+8 around its own pixel work
+        const bool lister = (warp == (i & (kLLook - 1))) && (i + kLLook < n);
+        ClsPend pend = ClsPend();
+        int pend_items = 0;
+        if (lister) pend = list_issue(i + kLLook, taps, pend_items);
+
+        mbar_wait(&s_lfull[i % kLSlots], (i / kLSlots) & 1);           // this tile's list
+        const unsigned short* list = s_list[i % kLSlots];
+        SFH_TLS(1, 1);
         Homog Hm;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) Hm.h[k] = st.theta[k];
+        for (int k = 0; k < 9; ++k) Hm.h[k] = s_theta[9 * b + k];
+        const unsigned char* s_tile = s_dyn + (size_t)s * kLStageBytes;
+        const size_t base_b = (size_t)b * H * W;
+        float* outb = p.out_f ? p.out_f + base_b : nullptr;
+        bool had_edge = false;
+
+        mbar_wait(&s_full[s], (i / kLS) & 1);                          // gt tile has landed
+        SFH_TLS(1, 2); SFH_TLS(0, 6);
 #define SFH_PIX_OK(j) (FT || (row_ok && col + (j) < W))
-        // rotate the starting patch with the tile index so the 32 % 15 remainder is shared out
-        int q = cw + (it % kPCons);
-        if (q >= kPCons) q -= kPCons;
+        // Dealing: list entries [0, E) touch a class edge (per-pixel path, ~10x the cost of an
+        // edge-free patch).  They go round-robin to warps 1..7 with an offset that continues
+        // across tiles (erot = edge patches dealt so far mod 7), so every warp gets the same
+        // share over time; warp 0 keeps to edge-free patches and is never late for its producer
+        // duty.  A warp first consumes everything it needs from the staged gt tile (edge-free
+        // patches are finished, edge patches keep their 128 class ids in one register per patch),
+        // releases the stage, and only then does the per-pixel work, which therefore overlaps the
+        // refill of the stage and the other warps' streaming.
+        const int E = s_lcount[i % kLSlots];
+        int q0 = (warp - 1) - erot;                                    // first edge entry of this warp
+        if (q0 < 0) q0 += kWarps - 1;
+        if (warp == 0) q0 = E;
+        erot = (erot + E) % (kWarps - 1);
+        unsigned stash[kLStash];
+        bool fits = true;                                              // every gt value of my edge patches is in 0..255
+#pragma unroll
+        for (int k = 0; k < kLStash; ++k) {
+            stash[k] = 0u;
+            const int q = q0 + k * (kWarps - 1);
+            if (q < E) {
+                const unsigned item = list[q];
+                const int soff = (((item & 0xffu) >> 3) * 8 + ly) * kTileW + (item & 7u) * kPatchW + lx * 4;
+                if (p.gt8) {
+                    stash[k] = *reinterpret_cast<const unsigned*>(s_tile + soff);
+                } else {
+                    const longlong2* sp2 = reinterpret_cast<const longlong2*>(reinterpret_cast<const long long*>(s_tile) + soff);
+                    const longlong2 glo = sp2[0], ghi = sp2[1];
+                    const int g0 = (int)glo.x, g1 = (int)glo.y, g2 = (int)ghi.x, g3 = (int)ghi.y;
+                    fits &= ((unsigned)(g0 | g1 | g2 | g3) < 256u);
+                    stash[k] = (unsigned)g0 | ((unsigned)g1 << 8) | ((unsigned)g2 << 16) | ((unsigned)g3 << 24);
+                }
+            }
+        }
+        fits = __all_sync(0xffffffffu, fits);
 #pragma unroll 1
-        for (; q < nitems; q += kPCons) {
-            const unsigned item = st.items[q];
+        for (int q = E + warp; q < nitems; q += kWarps) {              // edge-free patches: constant, zero gradient
+            const unsigned item = list[q];
             const int pr = (item & 0xffu) >> 3, pk = item & 7u, pc = (int)(item >> 8) - 1;
             const int row = band0 + pr * 8 + ly;
             const int col = tx * kTileW + pk * kPatchW + lx * 4;
@@ -1005,31 +1069,66 @@ __global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_
             const int rowc = FT ? row : min(row, H - 1);
             const bool vec = FT || (p.vec4 && row_ok && col + 3 < W);
             const int off = rowc * W + col;
-            const longlong2* sp2 = reinterpret_cast<const longlong2*>(s_gt + pr * (8 * kTileW) + pk * kPatchW + lane_px);
-            const longlong2 glo = sp2[0], ghi = sp2[1];                 // zero-filled outside the image by TMA
-            const float gf[4] = {(float)(int)glo.x, (float)(int)glo.y, (float)(int)ghi.x, (float)(int)ghi.y};
+            const int soff = (pr * 8 + ly) * kTileW + pk * kPatchW + lx * 4;   // zero-filled outside the image by TMA
+            float gf[4];
+            if (p.gt8) {
+                const uchar4 g8 = *reinterpret_cast<const uchar4*>(s_tile + soff);
+                gf[0] = (float)g8.x; gf[1] = (float)g8.y; gf[2] = (float)g8.z; gf[3] = (float)g8.w;
+            } else {
+                const longlong2* sp2 = reinterpret_cast<const longlong2*>(reinterpret_cast<const long long*>(s_tile) + soff);
+                const longlong2 glo = sp2[0], ghi = sp2[1];
+                gf[0] = (float)(int)glo.x; gf[1] = (float)(int)glo.y; gf[2] = (float)(int)ghi.x; gf[3] = (float)(int)ghi.y;
+            }
+            const float cval = taps.class_value(pc);
+            if (outb) {
+                if (vec) __stcs((float4*)(outb + off), make_float4(cval, cval, cval, cval));
+                else
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) outb[off + j] = cval;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float tg = p.nc_pow2 ? __fmul_rn(gf[j], p.inv_nc) : __fdiv_rn(gf[j], ncf);
+                const float d = cval - tg;
+                float l = (KMSE || fabsf(d) < 1.0f) ? d * d : 2.0f * fabsf(d) - 1.0f;
+                if (!SFH_PIX_OK(j)) l = 0.f;
+                loss_sum += l;
+            }
+        }
+        __syncwarp();
+        SFH_TLS(1, 3);
+        if (fits && lane == 0) mbar_arrive(&s_empty[s]);                // stage may be refilled
+
+        // per-pixel path (patch touches a class edge), one pixel at a time as in k_fused
+#pragma unroll 1
+        for (int k = 0; k < kLStash; ++k) {
+            const int q = q0 + k * (kWarps - 1);
+            if (q >= E) break;
+            had_edge = true;
+            const unsigned item = list[q];
+            const int pr = (item & 0xffu) >> 3, pk = item & 7u;
+            const int row = band0 + pr * 8 + ly;
+            const int col = tx * kTileW + pk * kPatchW + lx * 4;
+            const bool row_ok = FT || row < H;
+            const int rowc = FT ? row : min(row, H - 1);
+            const bool vec = FT || (p.vec4 && row_ok && col + 3 < W);
+            const int off = rowc * W + col;
+            float gf[4];
+            if (fits) {
+                unsigned sv = stash[0];
+#pragma unroll
+                for (int kk = 1; kk < kLStash; ++kk) sv = (k == kk) ? stash[kk] : sv;
+                gf[0] = (float)(sv & 0xffu); gf[1] = (float)((sv >> 8) & 0xffu);
+                gf[2] = (float)((sv >> 16) & 0xffu); gf[3] = (float)(sv >> 24);
+            } else {                                                    // stage still held: read the ids again
+                const int soff = (pr * 8 + ly) * kTileW + pk * kPatchW + lx * 4;
+                const longlong2* sp2 = reinterpret_cast<const longlong2*>(reinterpret_cast<const long long*>(s_tile) + soff);
+                const longlong2 glo = sp2[0], ghi = sp2[1];
+                gf[0] = (float)(int)glo.x; gf[1] = (float)(int)glo.y; gf[2] = (float)(int)ghi.x; gf[3] = (float)(int)ghi.y;
+            }
             float tgt[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) tgt[j] = p.nc_pow2 ? __fmul_rn(gf[j], p.inv_nc) : __fdiv_rn(gf[j], ncf);
-
-            if (pc >= 0) {                                              // edge-free patch
-                const float cval = taps.class_value(pc);
-                if (outb) {
-                    if (vec) __stcs((float4*)(outb + off), make_float4(cval, cval, cval, cval));
-                    else
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) outb[off + j] = cval;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float d = cval - tgt[j];
-                    float l = (p.kind == SFH_LOSS_MSE || fabsf(d) < 1.0f) ? d * d : 2.0f * fabsf(d) - 1.0f;
-                    if (!SFH_PIX_OK(j)) l = 0.f;
-                    loss_sum += l;
-                }
-                continue;
-            }
-            // per-pixel path
             const float v = p.ys ? __ldg(p.ys + rowc) : mesh_coord(rowc, H);
             float u[4];
             if (FT && p.xs) {
@@ -1042,15 +1141,27 @@ __global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_
                     u[j] = p.xs ? __ldg(p.xs + cx) : mesh_coord(cx, W);
                 }
             }
-            Pix px[4];
-            TapVals t[4];
-            float o[4], g[4];
+            float o[4];
+            bool any = false;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                px[j] = pixel_geom<SFH_MODE_BILINEAR>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]),
-                                                      __fmul_rn(u[j], Hm.h[6]), v, Wc_f, Hc_f);
-                t[j] = taps.fetch4(0, px[j].x0, px[j].y0);
-                o[j] = bilerp(px[j], t[j]);
+                const Pix qx = pixel_geom<SFH_MODE_BILINEAR>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]),
+                                                             __fmul_rn(u[j], Hm.h[6]), v, Wc_f, Hc_f);
+                const TapVals tv = taps.fetch4(0, qx.x0, qx.y0);
+                o[j] = bilerp(qx, tv);
+                const float d = o[j] - tgt[j];
+                float l, g;
+                if (KMSE || fabsf(d) < 1.0f) { l = d * d; g = d; }
+                else { l = 2.0f * fabsf(d) - 1.0f; g = d > 0.f ? 1.0f : -1.0f; }
+                if (!SFH_PIX_OK(j)) { l = 0.f; g = 0.f; }
+                loss_sum += l;
+                if (__any_sync(0xffffffffu, !tv.uni)) {
+                    g *= gscale;
+                    const float gix = ((tv.b - tv.a) * qx.sy + (tv.d - tv.c) * qx.ny) * g;
+                    const float giy = ((tv.c - tv.a) * qx.ex + (tv.d - tv.b) * qx.wx) * g;
+                    acc.add(qx, gix, giy, halfWc, halfHc, u[j]);
+                    any = true;
+                }
             }
             if (outb) {
                 if (vec) __stcs((float4*)(outb + off), make_float4(o[0], o[1], o[2], o[3]));
@@ -1058,74 +1169,75 @@ __global__ void __launch_bounds__(kPThreads, 1) k_train_persistent(const __grid_
 #pragma unroll
                     for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) outb[off + j] = o[j];
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float d = o[j] - tgt[j];
-                float l;
-                if (p.kind == SFH_LOSS_MSE || fabsf(d) < 1.0f) { l = d * d; g[j] = d; }
-                else { l = 2.0f * fabsf(d) - 1.0f; g[j] = d > 0.f ? 1.0f : -1.0f; }
-                if (!SFH_PIX_OK(j)) { l = 0.f; g[j] = 0.f; }
-                loss_sum += l;
-                g[j] *= gscale;
-            }
-            bool any = false;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (__any_sync(0xffffffffu, !t[j].uni)) {
-                    const float gix = ((t[j].b - t[j].a) * px[j].sy + (t[j].d - t[j].c) * px[j].ny) * g[j];
-                    const float giy = ((t[j].c - t[j].a) * px[j].ex + (t[j].d - t[j].b) * px[j].wx) * g[j];
-                    acc.add(px[j], gix, giy, halfWc, halfHc, u[j]);
-                    any = true;
-                }
-            }
             if (any) acc.end_row(v);
         }
 #undef SFH_PIX_OK
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[s]);                        // stage may be refilled
-        if (slot < 0) continue;
+        if (!fits) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[s]);
+        }
 
-        // ---- chunk boundary: this warp's sums go to the fixed slot (sample, chunk, warp) ----
-        float vals[16];
-        vals[0] = (p.kind != SFH_LOSS_MSE) ? 0.5f * loss_sum : loss_sum;
+        // ---- this warp's sums of this tile go to the fixed slot (tile, warp) ----
+        float* slot = p.partials + ((size_t)t * kWarps + warp) * kNPart;
+        const float lsum = KMSE ? loss_sum : 0.5f * loss_sum;
+        if (had_edge) {                                                 // warp-uniform
+            float vals[16];
+            vals[0] = lsum;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) vals[1 + k] = acc.a[k];
+            for (int k = 0; k < 9; ++k) vals[1 + k] = acc.a[k];
 #pragma unroll
-        for (int k = 10; k < 16; ++k) vals[k] = 0.f;
-        const float tot = warp_reduce16(vals, lane);
-        const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-        if (!(lane & 1) && idx < kNPart) p.partials[((size_t)slot * kPCons + cw) * kNPart + idx] = tot;
-        acc.zero();
+            for (int k = 10; k < 16; ++k) vals[k] = 0.f;
+            const float tot = warp_reduce16(vals, lane);
+            const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if (!(lane & 1) && idx < kNPart) slot[idx] = tot;
+            acc.zero();
+        } else {                                                        // only the loss is non-zero
+            const float tot = warp_sum(lsum);
+            if (lane < kNPart) slot[lane] = lane == 0 ? tot : 0.f;
+        }
         loss_sum = 0.f;
+
+        SFH_TLS(1, 4); SFH_TLS(0, 7);
+        if (lister) list_finish(i + kLLook, pend, pend_items);
+        // next tile of this CTA
+        t += G;
+        tx += dX;
+        int carry = tx >= tiles_x;
+        tx -= carry * tiles_x;
+        ty += dY + carry;
+        carry = ty >= tiles_y;
+        ty -= carry * tiles_y;
+        b += dB + carry;
     }
 }
 
-// Second stage of the persistent path: one CTA per sample adds that sample's (chunk, warp) slots in
+// Second stage of the streaming path: one CTA per sample adds that sample's (tile, warp) slots in
 // fixed order in fp64, then the optional weighting + batch mean + total dtheta (last CTA by ticket).
-__global__ void __launch_bounds__(kThreads) k_train_finalize(const __grid_constant__ FusedParams p) {
-    __shared__ double s_fin[kNPart][kFinGroup];
+constexpr int kFinThreads = 288;                 // 3 float4 columns of a slot x 96 slot lanes
+__global__ void __launch_bounds__(kFinThreads) k_train_finalize(const __grid_constant__ FusedParams p) {
+    __shared__ double s_w[kFinThreads / 32][4];
     __shared__ double s_out[kNPart];
     const int b = blockIdx.x, H = p.H, W = p.W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tiles_x = (W + kTileW - 1) / kTileW;
-    const int tiles_per_sample = tiles_x * ((H + 8 * kPR - 1) / (8 * kPR));
-    const int nslots = ((tiles_per_sample + kPChunk - 1) / kPChunk) * kPCons;
-    if (b == 0 && threadIdx.x == 0) p.counters[p.B + 1] = 0;           // chunk ticket for the next launch
+    const int nslots = p.fin_slots;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: the producer grid has completed
     {
-        const int k = threadIdx.x / kFinGroup, jj = threadIdx.x % kFinGroup;
-        if (k < kNPart) {
-            double s = 0.0;
-            const float* base = p.partials + (size_t)b * nslots * kNPart + k;
-            for (int t = jj; t < nslots; t += kFinGroup) s += (double)base[(size_t)t * kNPart];
-            s_fin[k][jj] = s;
+        // thread (cq, g): float4 column cq of slots g, g+96, ...; all loads independent (one L2 round trip)
+        const int cq = threadIdx.x / 96, g = threadIdx.x % 96;
+        const float4* base = reinterpret_cast<const float4*>(p.partials + (size_t)b * nslots * kNPart) + cq;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 4
+        for (int t = g; t < nslots; t += 96) {
+            const float4 v = __ldcg(base + (size_t)t * (kNPart / 4));
+            a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
         }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+        if (lane == 0) { s_w[warp][0] = a0; s_w[warp][1] = a1; s_w[warp][2] = a2; s_w[warp][3] = a3; }
     }
     __syncthreads();
     if (threadIdx.x < kNPart) {
-        const int k = threadIdx.x;
-        double s = 0.0;
-#pragma unroll
-        for (int jj = 0; jj < kFinGroup; ++jj) s += s_fin[k][jj];
+        const int k = threadIdx.x, cq = k >> 2, c = k & 3;
+        double s = (s_w[3 * cq][c] + s_w[3 * cq + 1][c]) + s_w[3 * cq + 2][c];
         if (k == 0) { s = s / ((double)H * (double)W); p.Lb[b] = (float)s; }
         else if (k <= 9) p.J[9 * b + k - 1] = (float)s;
         s_out[k] = s;
@@ -1259,6 +1371,14 @@ __global__ void k_sat_cols(unsigned* S, int sp, int rows, int cols) {
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 constexpr int64_t kTicketBytes = 262400;   // (65535 + 3) int32 tickets, 256-aligned
 
+// partial slots per sample: k_fused at R = 1 (upper bound over R) or k_train_stream's (tile, warp) slots
+static int64_t partial_slots(int H, int W) {
+    const int64_t tx = (W + kTileW - 1) / kTileW;
+    const int64_t fused = tx * ((H + kWarps - 1) / kWarps);
+    const int64_t stream = tx * ((H + 8 * kLR - 1) / (8 * kLR)) * kWarps;
+    return fused > stream ? fused : stream;
+}
+
 static int check_template(const sfh_template* t) {
     if (!t || !t->data || t->height <= 0 || t->width <= 0) return SFH_E_BADARG;
     if (t->fmt == SFH_TMPL_F32) return t->channels >= 1 ? 0 : SFH_E_BADARG;
@@ -1300,11 +1420,6 @@ static int setup_ws(FusedParams& p, void* ws, int64_t ws_bytes) {
     p.counters = (int*)ws;                                             // [B+3]: samples, batch, tile ticket, done
     p.contrib = (double*)((char*)ws + kTicketBytes);                   // [B]
     p.partials = (float*)((char*)p.contrib + align_up((int64_t)p.B * 8, 256));
-    const int64_t tx = (p.W + kTileW - 1) / kTileW;
-    const int64_t ntiles = tx * ((p.H + kWarps - 1) / kWarps);
-    const int64_t nslots = ((tx * ((p.H + 8 * kPR - 1) / (8 * kPR)) + kPChunk - 1) / kPChunk) * kPCons;
-    const int64_t n = ntiles > nslots ? ntiles : nslots;
-    p.lists = (unsigned short*)((char*)p.partials + align_up((int64_t)p.B * n * kNPart * 4, 256));
     return 0;
 }
 
@@ -1326,10 +1441,13 @@ static int launch_fmt(const FusedParams& p, dim3 grid, size_t dyn, bool ft, cuda
 }
 
 template <int MODE, int EPI>
-static int launch_fused(const FusedParams& p, cudaStream_t st) {
-    if (p.B > 65535) return SFH_E_BADARG;
+static int launch_fused(const FusedParams& p_in, cudaStream_t st) {
+    if (p_in.B > 65535) return SFH_E_BADARG;
+    FusedParams p = p_in;
     const int tiles_x = (p.W + kTileW - 1) / kTileW;
     dim3 grid(tiles_x, p.ntiles / tiles_x, p.B);
+    static const bool no_remap = getenv("SFH_NO_REMAP") != nullptr;
+    p.short_last = (!no_remap && grid.y > 1 && (p.H % (8 * p.rows_per_warp)) != 0) ? 1 : 0;
     const bool ft = p.vec4 && (p.W % kTileW == 0) && (p.H % 8 == 0) &&
                     (!p.xs || (((uintptr_t)p.xs & 15u) == 0));
     const size_t dyn = !p.use_tma ? 0
@@ -1343,38 +1461,61 @@ static int launch_fused(const FusedParams& p, cudaStream_t st) {
     }
 }
 
-template <int FMT>
-static int launch_persistent_fmt(const FusedParams& p, bool ft, int ctas, cudaStream_t st) {
-    auto kf = k_train_persistent<FMT, true>;
-    auto kg = k_train_persistent<FMT, false>;
-    const size_t dyn = (size_t)kPStages * kPTileBytes;
-    static bool raised = false;
-    if (!raised) {
-        cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        raised = true;
-    }
-    const int total_tiles = p.ntiles * p.B;
-    k_classify<FMT><<<(total_tiles + kWarps - 1) / kWarps, kThreads, 0, st>>>(p);
-    if (ft) kf<<<ctas, kPThreads, dyn, st>>>(p);
-    else    kg<<<ctas, kPThreads, dyn, st>>>(p);
-    k_train_finalize<<<p.B, kThreads, 0, st>>>(p);
-    return (int)cudaGetLastError();
+// k_train_finalize as a programmatically dependent launch: it may become resident while the
+// producer grid drains and waits in griddepcontrol.wait, which hides its launch latency.
+static int launch_finalize(const FusedParams& p, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.B); cfg.blockDim = dim3(kFinThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    static const bool no_pdl = getenv("SFH_NO_PDL") != nullptr;
+    if (no_pdl) cfg.numAttrs = 0;
+    return (int)cudaLaunchKernelEx(&cfg, k_train_finalize, p);
 }
 
-static int launch_persistent(const FusedParams& p, cudaStream_t st) {
+template <int FMT, bool KMSE>
+static int launch_stream_fmt(const FusedParams& p, bool ft, int sms, size_t dyn, cudaStream_t st) {
+    auto kf = k_train_stream<FMT, true, KMSE>;
+    auto kg = k_train_stream<FMT, false, KMSE>;
+    static size_t raised = 0;                  // per instantiation; idempotent, so a race is harmless
+    static int per_sm = 0;
+    if (dyn > raised || !per_sm) {
+        cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, kThreads, dyn) != cudaSuccess || occ < 1) occ = 1;
+        per_sm = occ;
+        raised = dyn;
+    }
+    const int total = p.ntiles * p.B;
+    const int resident = sms * per_sm;
+    const int ctas = total < resident ? total : resident;
+    if (ft) kf<<<ctas, kThreads, dyn, st>>>(p);
+    else    kg<<<ctas, kThreads, dyn, st>>>(p);
+    const int rc = (int)cudaGetLastError();
+    return rc ? rc : launch_finalize(p, st);
+}
+
+template <int FMT>
+static int launch_stream_kind(const FusedParams& p, bool ft, int sms, size_t dyn, cudaStream_t st) {
+    return p.kind == SFH_LOSS_MSE ? launch_stream_fmt<FMT, true>(p, ft, sms, dyn, st)
+                                  : launch_stream_fmt<FMT, false>(p, ft, sms, dyn, st);
+}
+
+static int launch_stream(const FusedParams& p, cudaStream_t st) {
     static const int sms = [] {
         int dev = 0, n = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         return n;
     }();
-    const int chunks = ((p.ntiles + kPChunk - 1) / kPChunk) * p.B;
-    const int ctas = chunks < sms ? chunks : sms;
     const bool ft = p.vec4 && (p.W % kTileW == 0) && (p.H % 8 == 0) && (!p.xs || (((uintptr_t)p.xs & 15u) == 0));
+    const size_t dyn = (size_t)kLS * kLStageBytes + (size_t)p.B * 9 * sizeof(float);
     switch (p.t.fmt) {
-        case SFH_TMPL_F32: return launch_persistent_fmt<SFH_TMPL_F32>(p, ft, ctas, st);
-        case SFH_TMPL_Q2:  return launch_persistent_fmt<SFH_TMPL_Q2>(p, ft, ctas, st);
-        case SFH_TMPL_Q4:  return launch_persistent_fmt<SFH_TMPL_Q4>(p, ft, ctas, st);
+        case SFH_TMPL_F32: return launch_stream_kind<SFH_TMPL_F32>(p, ft, sms, dyn, st);
+        case SFH_TMPL_Q2:  return launch_stream_kind<SFH_TMPL_Q2>(p, ft, sms, dyn, st);
+        case SFH_TMPL_Q4:  return launch_stream_kind<SFH_TMPL_Q4>(p, ft, sms, dyn, st);
         default: return SFH_E_BADFMT;
     }
 }
@@ -1457,13 +1598,7 @@ const char* sfh_error_string(int code) {
 
 int64_t sfh_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
-    const int64_t tx = (W + kTileW - 1) / kTileW;
-    const int64_t ntiles = tx * ((H + kWarps - 1) / kWarps);                      // k_fused, R = 1 upper bound
-    const int64_t nslots = ((tx * ((H + 8 * kPR - 1) / (8 * kPR)) + kPChunk - 1) / kPChunk) * kPCons;   // k_train_persistent
-    const int64_t n = ntiles > nslots ? ntiles : nslots;
-    const int64_t lists = (int64_t)B * tx * ((H + 8 * kPR - 1) / (8 * kPR)) * kPItems * 2;   // patch lists, 64 B per tile
-    return kTicketBytes + align_up((int64_t)B * 8, 256) +
-           align_up((int64_t)B * n * kNPart * 4, 256) + lists;
+    return kTicketBytes + align_up((int64_t)B * 8, 256) + align_up((int64_t)B * partial_slots(H, W) * kNPart * 4, 256);
 }
 
 int sfh_template_pack(const float* tmpl, int Hc, int Wc, const float* palette_host, int n_palette,
@@ -1554,22 +1689,29 @@ int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* a
         p.rows_per_warp = 8;
         p.ntiles = ((a->W + kTileW - 1) / kTileW) * ((a->H + 63) / 64);
     }
-    // experimental persistent warp-specialised variant (opt-in until it beats k_fused: with 3 x 64 KiB
-    // gt stages the L1 carve-out left for the template taps is too small — see DESIGN.md §4)
-    static const bool persist = getenv("SFH_PERSISTENT") != nullptr;
-    if (persist && !p.gt8) {
-        // persistent warp-specialised kernel: 128 x 64 tiles, one CTA per SM
+    // experimental streaming kernel (persistent tile loop; opt-in until it beats k_fused: measured
+    // 79 us vs 61 us on C2)
+    static const bool use_stream = getenv("SFH_STREAM") != nullptr;
+    if (use_stream && a->B <= kLMaxB) {
         FusedParams q = p;
-        q.rows_per_warp = kPR;
-        q.ntiles = ((a->W + kTileW - 1) / kTileW) * ((a->H + 8 * kPR - 1) / (8 * kPR));
+        q.rows_per_warp = kLR;
+        q.ntiles = ((a->W + kTileW - 1) / kTileW) * ((a->H + 8 * kLR - 1) / (8 * kLR));
+        q.fin_slots = q.ntiles * kWarps;
         if (make_gt_map(q)) {
             q.use_tma = 1;
-            return launch_persistent(q, (cudaStream_t)stream);
+            return launch_stream(q, (cudaStream_t)stream);
         }
     }
     p.use_tma = make_gt_map(p) ? 1 : 0;
-    return a->kind == SFH_LOSS_MSE ? launch_fused<SFH_LOSS_MSE, kEpiLoss>(p, (cudaStream_t)stream)
-                                   : launch_fused<SFH_LOSS_SMOOTHL1, kEpiLoss>(p, (cudaStream_t)stream);
+    // the per-sample / batch reduction runs as a second, programmatically dependent launch: the
+    // main kernel's CTAs then retire without a ticket (no MEMBAR.GPU per CTA, no serial tail)
+    static const bool one_launch = getenv("SFH_ONE_LAUNCH") != nullptr;
+    p.split_finalize = one_launch ? 0 : 1;
+    p.fin_slots = p.ntiles;
+    rc = a->kind == SFH_LOSS_MSE ? launch_fused<SFH_LOSS_MSE, kEpiLoss>(p, (cudaStream_t)stream)
+                                 : launch_fused<SFH_LOSS_SMOOTHL1, kEpiLoss>(p, (cudaStream_t)stream);
+    if (rc || !p.split_finalize) return rc;
+    return launch_finalize(p, (cudaStream_t)stream);
 }
 
 int sfh_predict_tail(const sfh_template* tmpl, const sfh_predict_tail_args* a, void* stream) {

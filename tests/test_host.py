@@ -43,9 +43,8 @@ def test_abi_metadata_and_argument_errors_without_gpu():
     assert l.sfh_error_string(0) == b"success"
     assert b"workspace" in l.sfh_error_string(-4)
     # workspace size is pure host arithmetic: a fixed 262400-byte ticket area, B doubles (256-aligned),
-    # 12 floats per partial slot (max of one per 128x8 tile / 15 per chunk of six 128x32 tiles),
-    # and a 64-byte patch list per 128x32 tile
-    assert l.sfh_workspace_bytes(64, 360, 640) == 262400 + 512 + 64 * max(5 * 45, 10 * 15) * 12 * 4 + 64 * 5 * 12 * 64
+    # 12 floats per partial slot (max of one per 128x8 tile / 8 per 128x32 tile of the streaming kernel)
+    assert l.sfh_workspace_bytes(64, 360, 640) == 262400 + 512 + 64 * max(5 * 45, 5 * 12 * 8) * 12 * 4
     assert l.sfh_workspace_bytes(0, 360, 640) == 0
     # argument validation happens before any CUDA call
     assert l.sfh_warp_fwd(None, None, None, None, 1, 1, 1, 0, None, None) < 0

@@ -9,11 +9,16 @@ Tolerances (BASELINE.json north_star):
   warped float masks  <= 1e-5 abs         int / nearest masks  bit-exact
   POI                 <= 1e-4 px          dtheta               <= 1e-4 relative (per-sample norm)
 """
+import json
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from conftest import unpack2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -504,6 +509,54 @@ def test_workspace_reuse_across_batch_sizes():
         assert abs(float(r["loss"]) - expect) <= 1e-6 * abs(expect), (B, float(r["loss"]), expect)
         ref.setdefault(B, float(r["loss"]))
         assert ref[B] == float(r["loss"])
+
+
+def test_alternative_launch_paths_agree():
+    """The training tail has three launch shapes (selected per process by environment variables):
+    k_fused + k_train_finalize (default), k_fused alone with in-kernel tickets (SFH_ONE_LAUNCH) and the
+    experimental persistent tile loop (SFH_STREAM).  They must give the same warp mask bit for bit and
+    the same sums up to fp32 summation order."""
+    import subprocess
+    import sys
+    code = r"""
+import sys, json, torch
+sys.path.insert(0, %r)
+import sfh_b200
+from sfh_b200 import synth
+dev = torch.device('cuda:0')
+out = {}
+for (W, H, B, kind) in [(640, 360, 9, 'MSE'), (200, 77, 5, 'SmoothL1'), (1280, 720, 3, 'MSE')]:
+    tmpl, poi = sfh_b200.load_bundled('ncaa_nc4', (1280, 720) if W > 640 else (640, 360), 4, 1)
+    st = sfh_b200.STNWarpStage(tmpl.to(dev), poi.to(dev), (W, H), 4)
+    stn = sfh_b200.STNWarpStage(tmpl.to(dev), poi.to(dev), (W, H), 4, warp_with_nearest=True)
+    th = synth.theta_family_b(B, 3).to(dev)
+    gt = stn.predict_tail(synth.perturb(th.cpu(), seed=1).to(dev), None, False, False)['warp_mask'].to(torch.int64)
+    gp = st.transform_poi(synth.perturb(th.cpu(), seed=2).to(dev)).detach()
+    nz = torch.ones(B, poi.shape[1], device=dev)
+    w = torch.rand(B, generator=torch.Generator().manual_seed(5)).double().to(dev)
+    for rep in range(2):                       # second call: the workspace is reused
+        r = st.train_step(th, gt, w, kind, gp, nz, nz.sum(1), 1.0, 8.0, True, {})
+    torch.cuda.synchronize()
+    out['%%dx%%d' %% (W, H)] = dict(loss=float(r['loss']), mask=float(r['warp_mask'].double().sum()),
+                                mask_sq=float((r['warp_mask'].double() ** 2).sum()),
+                                rec=r['rec_per_sample'].double().cpu().tolist(), dth=r['dtheta'].double().flatten().cpu().tolist())
+print('RESULT' + json.dumps(out))
+""" % ROOT
+    res = {}
+    for name, env in (("default", {}), ("one_launch", {"SFH_ONE_LAUNCH": "1"}), ("stream", {"SFH_STREAM": "1"})):
+        e = dict(os.environ)
+        e.update(env)
+        pr = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
+        assert pr.returncode == 0, pr.stderr[-2000:]
+        res[name] = json.loads([l for l in pr.stdout.splitlines() if l.startswith("RESULT")][0][6:])
+    for name in ("one_launch", "stream"):
+        for cfg, a in res["default"].items():
+            b = res[name][cfg]
+            assert a["mask"] == b["mask"] and a["mask_sq"] == b["mask_sq"], (name, cfg)
+            assert abs(a["loss"] - b["loss"]) <= 1e-6 * abs(a["loss"]), (name, cfg, a["loss"], b["loss"])
+            np.testing.assert_allclose(b["rec"], a["rec"], rtol=1e-6, atol=1e-9)
+            scale = max(abs(x) for x in a["dth"])
+            np.testing.assert_allclose(b["dth"], a["dth"], rtol=0, atol=1e-5 * scale)
 
 
 # ---------------------------------------------------------------------- API / error conventions

@@ -44,3 +44,24 @@ d = (t[:, 6] - t[:, 0]) / 1e3
 print(f"{'CTA lifetime':52s} median {np.median(d):6.2f} us  p90 {np.percentile(d, 90):6.2f}  max {d.max():6.2f}")
 starts = np.sort(t[:, 0] - t0) / 1e3
 print("CTA start times us: 10%%=%.1f 50%%=%.1f 90%%=%.1f last=%.1f" % tuple(np.percentile(starts, [10, 50, 90, 100])))
+
+# per-SM view: how many CTAs each SM ran, and how long a freed slot stays empty before the next CTA starts
+sm = t[:, 7].astype(int)
+gaps, per_sm, busy = [], [], []
+span = (t[:, 6].max() - t0)
+for m in np.unique(sm):
+    c = t[sm == m]
+    per_sm.append(len(c))
+    ends = sorted(c[:, 6].tolist())
+    for s_ in sorted(c[:, 0].tolist()):
+        prev = [e for e in ends if e <= s_]
+        if prev:
+            e = max(prev)
+            ends.remove(e)
+            gaps.append((s_ - e) / 1e3)
+    busy.append((c[:, 6] - c[:, 0]).sum() / span)
+print("SMs %d  CTAs/SM min %d median %d max %d" % (len(per_sm), min(per_sm), int(np.median(per_sm)), max(per_sm)))
+print("slot refill gap us: median %.2f p90 %.2f max %.2f (n=%d)" % (np.median(gaps), np.percentile(gaps, 90), max(gaps), len(gaps)))
+print("average resident CTAs per SM over the kernel span: median %.2f min %.2f" % (np.median(busy), min(busy)))
+ends_all = np.sort(t[:, 6] - t0) / 1e3
+print("CTA end times us: 50%%=%.1f 90%%=%.1f 99%%=%.1f last=%.1f" % tuple(np.percentile(ends_all, [50, 90, 99, 100])))
