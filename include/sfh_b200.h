@@ -206,6 +206,19 @@ int sfh_reproj_loss(const float* inputs, const float* targets, const float* nonz
                     const float* num_nonzero, int B, int N, float* R_b,
                     const float* grad_Rb, float* dinputs, void* stream);
 
+/* Training / evaluation consistency loss — train.py:219-223, eval.py:201-203:
+ *   loss = lambda * CrossEntropyLoss(reduction='mean')(logits, (warp_mask * nc).long())
+ * warp_mask [B,1,H,W] fp32 (what sfh_warp_fwd / sfh_warp_loss_fwd_bwd wrote), logits [B,nc,H,W]
+ * fp32 of the SAME size (the training configuration), 1 <= nc <= 8.  loss_out: device scalar.
+ * dlogits [B,nc,H,W] (nullable) = d loss / d logits = lambda/(B*H*W) * (softmax - onehot).
+ * No gradient flows to theta (the integer cast cuts it, as in the reference).  Class ids outside
+ * [0,nc) are clamped.  workspace: >= sfh_consist_workspace_bytes() bytes, zero before the first
+ * call (the library leaves it zeroed). */
+int64_t sfh_consist_workspace_bytes(void);
+int sfh_consist_loss_fwd_bwd(const float* warp_mask, const float* logits, int B, int nc, int H, int W,
+                             float lambda, float* loss_out, float* dlogits,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Diagnostic: exhaustively compares the kernels' fast correctly-rounded reciprocal with IEEE
  * rcp.rn over every fp32 value with |z| in (1e-8, 1e37) (the range it is used on; the warp path
  * falls back to rcp.rn outside).  *mismatches (device uint64, pre-zeroed) receives the count. */

@@ -179,3 +179,14 @@ def rec_loss_per_sample(warp_mask, gt_masks, mask_classes: int, kind: str = "MSE
     else:
         raise NotImplementedError(kind)
     return torch.mean(ell, dim=(1, 2))
+
+
+def consistency_loss(logits, warp_mask, num_classes: int, consist_lambda: float = 1.0):
+    """train.py:219-223 (and the eval metric, eval.py:201-203): CE between the segmentation logits and
+    the class mask obtained by truncating the warped template, ``nn.CrossEntropyLoss()`` defaults
+    (reduction 'mean' over every pixel of the batch).  ``warp_mask`` is [B,1,H,W] as the warper
+    returns it; train.py indexes it the same way through the squeeze in Reconstructor.forward."""
+    rec_masks_int = (warp_mask * num_classes).to(dtype=torch.long)
+    if rec_masks_int.ndim == 4:
+        rec_masks_int = rec_masks_int[:, 0]
+    return F.cross_entropy(logits, rec_masks_int) * consist_lambda

@@ -73,3 +73,81 @@ def weight_and_reduce(per_sample_loss, per_sample_weights):
     """Last two lines of per_sample_weighted_criterion (models/losses.py:38-39) applied to an
     already-reduced per-sample loss: ``mean(L_b * w)`` with plain broadcasting."""
     return torch.mean(per_sample_loss * per_sample_weights)
+
+
+# ---------------------------------------------------------------------------------------------
+# Consistency loss (SURVEY.md §8 f-2): train.py:219-223, eval.py:201-203
+# ---------------------------------------------------------------------------------------------
+_CONSIST_WS = {}
+
+
+def _consist_ws(device):
+    """Small per-(device, stream) workspace: one ticket + one fp32 partial per CTA; allocated zeroed,
+    left zeroed by the kernel."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _CONSIST_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_lib.lib().sfh_consist_workspace_bytes()), dtype=torch.uint8, device=device)
+        _CONSIST_WS[key] = ws
+    return ws
+
+
+def _check_consist_args(logits, warp_mask, num_classes):
+    for name, t in (("logits", logits), ("warp_mask", warp_mask)):
+        if not isinstance(t, torch.Tensor) or t.dtype != torch.float32 or not t.is_cuda:
+            raise TypeError(f"{name} must be a float32 CUDA tensor")
+    if logits.ndim != 4 or logits.shape[1] != num_classes:
+        raise ValueError("logits must be [B,num_classes,H,W]")
+    B, _, H, W = logits.shape
+    if warp_mask.numel() != B * H * W or tuple(warp_mask.shape[-2:]) != (H, W):
+        raise ValueError("warp_mask must be [B,1,H,W] (or [B,H,W]) with the logits' H, W")
+    if not 1 <= num_classes <= 8:
+        raise ValueError("num_classes must be in 1..8")
+
+
+def consistency_step(logits, warp_mask, num_classes, consist_lambda=1.0, need_grad=True, out=None):
+    """``consist_lambda * CrossEntropyLoss()(logits, (warp_mask * num_classes).long())`` and its
+    gradient w.r.t. ``logits`` in ONE streaming launch (no log_softmax tensor, no int64 mask).
+    Returns ``{"loss": scalar tensor, "dlogits": [B,nc,H,W] or None}``; ``out`` reuses buffers."""
+    _check_consist_args(logits, warp_mask, num_classes)
+    B, nc, H, W = logits.shape
+    logits = logits.contiguous()
+    warp_mask = warp_mask.contiguous()
+    out = {} if out is None else out
+    loss = out.get("loss")
+    if loss is None or loss.device != logits.device:
+        loss = out["loss"] = torch.empty((), dtype=torch.float32, device=logits.device)
+    dl = None
+    if need_grad:
+        dl = out.get("dlogits")
+        if dl is None or dl.shape != logits.shape or dl.device != logits.device:
+            dl = out["dlogits"] = torch.empty_like(logits)
+    ws = _consist_ws(logits.device)
+    with torch.cuda.device(logits.device):
+        rc = _lib.lib().sfh_consist_loss_fwd_bwd(warp_mask.data_ptr(), logits.data_ptr(), B, nc, H, W,
+                                                 float(consist_lambda), loss.data_ptr(),
+                                                 dl.data_ptr() if dl is not None else None,
+                                                 ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "sfh_consist_loss_fwd_bwd")
+    return {"loss": loss, "dlogits": dl}
+
+
+class _ConsistFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, warp_mask, num_classes, consist_lambda):
+        r = consistency_step(logits, warp_mask, num_classes, consist_lambda, need_grad=logits.requires_grad)
+        ctx.dl = r["dlogits"]
+        return r["loss"].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        dl, ctx.dl = ctx.dl, None
+        if dl is None:
+            return None, None, None, None
+        return dl.mul_(g.to(torch.float32)), None, None, None      # in place: the buffer is ours
+
+
+def consistency_loss(logits, warp_mask, num_classes, consist_lambda=1.0):
+    """Differentiable (w.r.t. ``logits``) form of train.py:221-222; no gradient reaches ``warp_mask``
+    — the reference's ``.to(dtype=torch.long)`` cuts it the same way."""
+    return _ConsistFn.apply(logits, warp_mask.detach(), int(num_classes), float(consist_lambda))

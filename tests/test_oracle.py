@@ -241,3 +241,18 @@ def test_reference_shape_conventions():
     assert torch.equal(kr.transform_points(th, pts), kr.transform_points(th[:, None], pts))
     with pytest.raises(ValueError):
         kr.transform_points(th[:2], pts)
+
+
+def test_consistency_loss_restatement_closed_form():
+    """train.py:219-223: uniform logits give log(nc) whatever the mask; a confident correct prediction
+    gives ~0; truncation maps values between two class levels to the lower class."""
+    import math
+    from oracle import kornia_restated as kr
+    B, nc, H, W = 2, 4, 5, 7
+    warp = torch.randint(0, nc, (B, 1, H, W)).float() / nc
+    assert abs(float(kr.consistency_loss(torch.zeros(B, nc, H, W), warp, nc)) - math.log(nc)) < 1e-6
+    cls = (warp * nc).long()[:, 0]
+    conf = torch.nn.functional.one_hot(cls, nc).permute(0, 3, 1, 2).float() * 50.0
+    assert float(kr.consistency_loss(conf, warp, nc, 3.0)) < 1e-6
+    assert float(kr.consistency_loss(conf, warp + 0.2 / nc, nc)) < 1e-6          # still the same class after trunc
+    assert float(kr.consistency_loss(conf, warp[:, 0], nc)) < 1e-6                # [B,H,W] accepted

@@ -559,6 +559,51 @@ print('RESULT' + json.dumps(out))
             np.testing.assert_allclose(b["dth"], a["dth"], rtol=0, atol=1e-5 * scale)
 
 
+@pytest.mark.parametrize("W,H,B,nc", [(640, 360, 64, 4), (640, 360, 3, 4), (200, 77, 5, 4), (130, 50, 2, 3), (1280, 720, 2, 4)])
+def test_consistency_loss_matches_torch_cross_entropy(W, H, B, nc):
+    """SURVEY §8 f-2 — train.py:219-223: lambda * CE(logits, (warp_mask*nc).long()) and d/dlogits, one launch."""
+    g = torch.Generator().manual_seed(W + B)
+    logits = (torch.randn(B, nc, H, W, generator=g) * 3.0)
+    cls = torch.randint(0, nc, (B, 1, H, W), generator=g)
+    warp = cls.float() / nc
+    warp[0, 0, :2, :8] += 0.1                                   # values between class levels truncate down
+    lam = 0.7
+    lr = logits.clone().double().requires_grad_(True)
+    ref = kr.consistency_loss(lr, warp.double(), nc, lam)
+    ref.backward()
+    r = sfh_b200.consistency_step(logits.to(DEV), warp.to(DEV), nc, lam)
+    assert abs(float(r["loss"]) - float(ref)) <= 1e-5 * abs(float(ref))
+    gs = float(lr.grad.abs().max())
+    assert float((r["dlogits"].cpu().double() - lr.grad).abs().max()) <= 2e-6 * gs
+    # forward only (the eval metric, eval.py:201-203) and the autograd wrapper with an upstream factor
+    r0 = sfh_b200.consistency_step(logits.to(DEV), warp.to(DEV), nc, lam, need_grad=False)
+    assert r0["dlogits"] is None and float(r0["loss"]) == float(r["loss"])
+    lg = logits.to(DEV).requires_grad_(True)
+    (sfh_b200.consistency_loss(lg, warp.to(DEV), nc, lam) * 2.5).backward()
+    assert float((lg.grad.cpu().double() - 2.5 * lr.grad).abs().max()) <= 2e-6 * 2.5 * gs
+    # run-to-run determinism
+    r2 = sfh_b200.consistency_step(logits.to(DEV), warp.to(DEV), nc, lam)
+    assert float(r2["loss"]) == float(r["loss"]) and torch.equal(r2["dlogits"], r["dlogits"])
+
+
+def test_consistency_loss_on_the_warp_stage_output():
+    """End to end as train.py uses it: the mask comes from the fused train tail."""
+    tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 1)
+    st = mk_stage(tmpl.to(DEV), poi.to(DEV), (640, 360), 4)
+    B = 4
+    th = _thetas("a", B, 3).to(DEV)
+    gt = torch.zeros(B, 360, 640, dtype=torch.int64, device=DEV)
+    wm = st.train_step(th, gt, torch.ones(B, dtype=torch.float64, device=DEV), "MSE")["warp_mask"]
+    logits = torch.randn(B, 4, 360, 640, generator=torch.Generator().manual_seed(1)).to(DEV)
+    ref = kr.consistency_loss(logits.cpu(), wm.cpu(), 4)
+    got = sfh_b200.consistency_loss(logits, wm, 4)
+    assert abs(float(got) - float(ref)) <= 1e-5 * abs(float(ref))
+    with pytest.raises(ValueError):
+        sfh_b200.consistency_step(logits[:, :3], wm, 4)
+    with pytest.raises(TypeError):
+        sfh_b200.consistency_step(logits.cpu(), wm, 4)
+
+
 # ---------------------------------------------------------------------- API / error conventions
 def test_error_conventions_and_state_dict():
     tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 2)

@@ -72,6 +72,12 @@ for (W, H, B) in cfgs:
         run(f"predict_{W}x{H}_B{B}", lambda i: stn.predict_tail(S(i)["th"], S(i)["logits"], True, True, S(i)["outp"]), px * 4 + B * 4 * 360 * 640 * 4)
         run(f"predict_u8mask_{W}x{H}_B{B}", lambda i: stn.predict_tail(S(i)["th"], S(i)["logits"], True, True, S(i).setdefault("outp8", {}), torch.uint8), px * 1 + B * 4 * 360 * 640 * 4)
         run(f"predict_noscore_{W}x{H}_B{B}", lambda i: stn.predict_tail(S(i)["th"], None, False, False, S(i)["outp"]), px * 4)
+        if (W, H) == (640, 360):      # training configuration: logits at the warp size
+            for s_ in sets:
+                s_["wm"] = stb.warp(s_["th"])
+                s_["cons"] = {}
+            run(f"consist_ce+dlogits_{W}x{H}_B{B}", lambda i: sfh_b200.consistency_step(S(i)["logits"], S(i)["wm"], 4, 1.0, True, S(i)["cons"]), px * 4 + 2 * B * 4 * H * W * 4)
+            run(f"consist_ce_fwd_only_{W}x{H}_B{B}", lambda i: sfh_b200.consistency_step(S(i)["logits"], S(i)["wm"], 4, 1.0, False, S(i)["cons"]), px * 4 + B * 4 * H * W * 4)
         go = torch.randn(B, 1, H, W, device=dev)
         thg = S(0)["th"]
         def bwd(i):
