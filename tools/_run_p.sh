@@ -1,3 +1,4 @@
-echo default; timeout 300 python tools/kbench.py --hd --only predict
-echo NO_REMAP; SFH_NO_REMAP=1 timeout 300 python tools/kbench.py --hd --only predict
-echo NO_REMAP store;  SFH_NO_REMAP=1 timeout 300 python tools/kbench.py --hd --only store
+timeout 120 python tools/pcheck.py
+SFH_FLAT=1 timeout 120 python tools/pcheck.py
+SFH_FLAT=1 timeout 300 python tools/kbench.py --only train_ --hd
+SFH_FLAT=1 timeout 120 python tools/kbench.py --only train_640x --oob
