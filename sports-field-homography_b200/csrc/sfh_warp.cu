@@ -1211,267 +1211,6 @@ __global__ void __launch_bounds__(kThreads, SFH_STREAM_CTAS) k_train_stream(cons
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Flat training kernel: no tiles, no staging, no CTA-level phases.
-//
-// The unit of work is one BAND: 128 x 8 output pixels of one sample = 8 patches of 16 x 8.  Every
-// warp repeatedly takes the next band from a global ticket (prefetched one band ahead), so the
-// schedule is greedy and the tail is one band long.  Per band the warp
-//   1. computes the 18 patch-corner coordinates (one lane each), assembles the 8 bounding boxes
-//      by shuffle and asks the summed-area table which patches are free of class edges;
-//   2. streams the edge-free patches, up to four at a time: 128-bit loads of the int64 ground
-//      truth straight from global memory (eight in flight per lane), 128-bit stores of the
-//      constant class value, loss accumulation;
-//   3. runs the per-pixel path on the patches that touch a class edge;
-//   4. writes its 10 sums to the band's fixed slot (results do not depend on which warp ran it).
-// Warps of a CTA never synchronise after the prologue, so memory-bound (2) and issue-bound (3)
-// phases of different warps overlap on the SM; with nothing staged in shared memory the L1 keeps
-// the template, the edge table and theta.  k_train_finalize reduces the slots.
-// ------------------------------------------------------------------------------------------
-template <int FMT, bool FT, bool KMSE>
-__global__ void __launch_bounds__(kThreads, 3) k_train_flat(const __grid_constant__ FusedParams p) {
-    __shared__ __align__(16) float s_tab[Taps<FMT>::kSmemFloats];
-    const int H = p.H, W = p.W;
-    const int lane = threadIdx.x & 31;
-    const int lx = lane & 3, ly = lane >> 2;
-    const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
-    const int tiles_x = (W + kTileW - 1) / kTileW;
-    const int ups = p.ntiles;                                          // bands (units) per sample
-    const int total = ups * p.B;
-    int* ctr = p.counters + p.B + 1;
-
-    asm volatile("griddepcontrol.launch_dependents;");
-    int unit = 0;
-    if (lane == 0) unit = atomicAdd(ctr, 1);
-    Taps<FMT> taps;
-    taps.build_tables(p.t, s_tab);
-    __syncthreads();
-    taps.init(p.t, 0, s_tab);
-    unit = __shfl_sync(0xffffffffu, unit, 0);
-
-    const float halfWc = 0.5f * Wc_f, halfHc = 0.5f * Hc_f;
-    const float gscale = (KMSE ? 2.0f : 1.0f) * p.invN;
-    const float ncf = (float)p.nc;
-    const bool classify = (FMT != SFH_TMPL_F32) && (p.t.sat != nullptr);
-
-#pragma unroll 1
-    while (unit < total) {
-        int next = 0;
-        if (lane == 0) next = atomicAdd(ctr, 1);                       // consumed after this band
-        const int b = unit / ups, rem = unit - b * ups;
-        const int band = rem / tiles_x, tx = rem - band * tiles_x;
-        const int row0 = band * 8, col0 = tx * kTileW;
-        const int npatch = FT ? 8 : min(8, (W - col0 + kPatchW - 1) / kPatchW);
-        if (rem == 0 && p.poi.court_poi) poi_warp(p.poi, b, lane);    // the sample's court points (fp64)
-        Homog Hm;
-        Hm.load(p.theta + 9 * b);
-
-        // ---- 1. classification: lanes 0..17 hold the corner grid (2 rows x 9 columns) ----
-        unsigned edge_mask = (1u << npatch) - 1u;                      // bit k: patch k needs the per-pixel path
-        int cls = -1;                                                  // lane k: class of patch k when edge-free
-        if (classify) {
-            const int cr = lane >= 9 ? 1 : 0, ck = lane - 9 * cr;     // lanes 18..31 recompute corner (1, 9..): unused
-            const int grow = min(row0 + 8 * cr, H - 1), gcol = min(col0 + kPatchW * min(ck, 8), W - 1);
-            const float gu = p.xs ? __ldg(p.xs + gcol) : mesh_coord(gcol, W);
-            const float gv = p.ys ? __ldg(p.ys + grow) : mesh_coord(grow, H);
-            const Flow f = flow_at(Hm, __fmul_rn(gu, Hm.h[0]), __fmul_rn(gu, Hm.h[3]), __fmul_rn(gu, Hm.h[6]), gv);
-            const float gx = __fmul_rn(__fmaf_rn(__fadd_rn(f.x, 1.0f), Wc_f, -1.0f), 0.5f);
-            const float gy = __fmul_rn(__fmaf_rn(__fadd_rn(f.y, 1.0f), Hc_f, -1.0f), 0.5f);
-            const float gz = f.zok ? f.s : __int_as_float(0x7fc00000);                 // sign of Z; NaN poisons the patch
-            // patch k = lane: corners at lanes k, k+1, k+9, k+10
-            const int k0 = lane & 7;
-            const float x00 = __shfl_sync(0xffffffffu, gx, k0), x01 = __shfl_sync(0xffffffffu, gx, k0 + 1);
-            const float x10 = __shfl_sync(0xffffffffu, gx, k0 + 9), x11 = __shfl_sync(0xffffffffu, gx, k0 + 10);
-            const float y00 = __shfl_sync(0xffffffffu, gy, k0), y01 = __shfl_sync(0xffffffffu, gy, k0 + 1);
-            const float y10 = __shfl_sync(0xffffffffu, gy, k0 + 9), y11 = __shfl_sync(0xffffffffu, gy, k0 + 10);
-            const float z00 = __shfl_sync(0xffffffffu, gz, k0), z01 = __shfl_sync(0xffffffffu, gz, k0 + 1);
-            const float z10 = __shfl_sync(0xffffffffu, gz, k0 + 9), z11 = __shfl_sync(0xffffffffu, gz, k0 + 10);
-            if (lane < npatch) {
-                const float xmin = fminf(fminf(x00, x01), fminf(x10, x11)), xmax = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11));
-                const float ymin = fminf(fminf(y00, y01), fminf(y10, y11)), ymax = fmaxf(fmaxf(y00, y01), fmaxf(y10, y11));
-                const bool zpos = (z00 > 0.f) & (z01 > 0.f) & (z10 > 0.f) & (z11 > 0.f);
-                const bool zneg = (z00 < 0.f) & (z01 < 0.f) & (z10 < 0.f) & (z11 < 0.f);
-                const bool fin = (x00 == x00) & (x01 == x01) & (x10 == x10) & (x11 == x11) &
-                                 (y00 == y00) & (y01 == y01) & (y10 == y10) & (y11 == y11) &
-                                 (xmin > -1e9f) & (xmax < 1e9f) & (ymin > -1e9f) & (ymax < 1e9f);
-                if ((zpos | zneg) & fin) {
-                    const int wmax = p.t.width + 1, hmax = p.t.height + 1;
-                    const int i0 = min(max(__float2int_rd(xmin - kBoxMargin) + 1, 0), wmax);
-                    const int i1 = min(max(__float2int_rd(xmax + kBoxMargin) + 2, 0), wmax);
-                    const int j0 = min(max(__float2int_rd(ymin - kBoxMargin) + 1, 0), hmax);
-                    const int j1 = min(max(__float2int_rd(ymax + kBoxMargin) + 2, 0), hmax);
-                    const unsigned* S = p.t.sat;
-                    const int sp = p.t.sat_pitch;
-                    const unsigned ec = taps.entry_class(i0, j0);
-                    const unsigned cnt = __ldg(S + (j1 + 1) * sp + (i1 + 1)) - __ldg(S + j0 * sp + (i1 + 1))
-                                       - __ldg(S + (j1 + 1) * sp + i0) + __ldg(S + j0 * sp + i0);
-                    if (cnt == 0u) cls = (int)ec;
-                }
-            }
-            edge_mask = __ballot_sync(0xffffffffu, lane < npatch && cls < 0);
-        }
-
-        const int row = row0 + ly;
-        const bool row_ok = FT || row < H;
-        const int rowc = FT ? row : min(row, H - 1);
-        const size_t base = (size_t)b * H * W + (size_t)rowc * W + col0 + lx * 4;     // + 16 * k per patch
-        float loss_sum = 0.f;
-#define SFH_PIX_OK(j) (FT || (row_ok && col + (j) < W))
-
-        // ---- 2. edge-free patches, four at a time ----
-        unsigned fm = ((1u << npatch) - 1u) & ~edge_mask;
-#pragma unroll 1
-        while (fm) {
-            int ks[4];
-            Gt4 g[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                ks[u] = fm ? (__ffs(fm) - 1) : -1;
-                fm &= fm - 1u;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (ks[u] >= 0) {
-                    const int col = col0 + ks[u] * kPatchW + lx * 4;
-                    const bool vec = FT || (p.vec4 && row_ok && col + 3 < W);
-                    if (p.gt8) {
-                        uchar4 g8 = make_uchar4(0, 0, 0, 0);
-                        const unsigned char* gp = p.gt8 + base + ks[u] * kPatchW;
-                        if (vec) g8 = __ldcs(reinterpret_cast<const uchar4*>(gp));
-                        else {
-                            if (SFH_PIX_OK(0)) g8.x = gp[0];
-                            if (SFH_PIX_OK(1)) g8.y = gp[1];
-                            if (SFH_PIX_OK(2)) g8.z = gp[2];
-                            if (SFH_PIX_OK(3)) g8.w = gp[3];
-                        }
-                        g[u].lo.x = g8.x; g[u].lo.y = g8.y; g[u].hi.x = g8.z; g[u].hi.y = g8.w;
-                    } else {
-                        g[u] = load_gt<FT>(p.gt, base + ks[u] * kPatchW, col, W, vec, row_ok);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (ks[u] >= 0) {
-                    const int col = col0 + ks[u] * kPatchW + lx * 4;
-                    const bool vec = FT || (p.vec4 && row_ok && col + 3 < W);
-                    const int pc = __shfl_sync(0xffffffffu, cls, ks[u]);
-                    const float cval = taps.class_value(pc);
-                    if (p.out_f) {
-                        float* op = p.out_f + base + ks[u] * kPatchW;
-                        if (vec) __stcs((float4*)op, make_float4(cval, cval, cval, cval));
-                        else
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) op[j] = cval;
-                    }
-                    const float gf[4] = {(float)(int)g[u].lo.x, (float)(int)g[u].lo.y, (float)(int)g[u].hi.x, (float)(int)g[u].hi.y};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float tg = p.nc_pow2 ? __fmul_rn(gf[j], p.inv_nc) : __fdiv_rn(gf[j], ncf);
-                        const float d = cval - tg;
-                        float l = (KMSE || fabsf(d) < 1.0f) ? d * d : 2.0f * fabsf(d) - 1.0f;
-                        if (!SFH_PIX_OK(j)) l = 0.f;
-                        loss_sum += l;
-                    }
-                }
-            }
-        }
-
-        // ---- 3. patches on class edges: per-pixel homography + bilinear + chain rule ----
-        GradAcc acc;
-        acc.zero();
-        unsigned em = edge_mask;
-        const float v = p.ys ? __ldg(p.ys + rowc) : mesh_coord(rowc, H);
-#pragma unroll 1
-        while (em) {
-            const int k = __ffs(em) - 1;
-            em &= em - 1u;
-            const int col = col0 + k * kPatchW + lx * 4;
-            const bool vec = FT || (p.vec4 && row_ok && col + 3 < W);
-            float gf[4];
-            if (p.gt8) {
-                uchar4 g8 = make_uchar4(0, 0, 0, 0);
-                const unsigned char* gp = p.gt8 + base + k * kPatchW;
-                if (vec) g8 = __ldcs(reinterpret_cast<const uchar4*>(gp));
-                else {
-                    if (SFH_PIX_OK(0)) g8.x = gp[0];
-                    if (SFH_PIX_OK(1)) g8.y = gp[1];
-                    if (SFH_PIX_OK(2)) g8.z = gp[2];
-                    if (SFH_PIX_OK(3)) g8.w = gp[3];
-                }
-                gf[0] = (float)g8.x; gf[1] = (float)g8.y; gf[2] = (float)g8.z; gf[3] = (float)g8.w;
-            } else {
-                const Gt4 g = load_gt<FT>(p.gt, base + k * kPatchW, col, W, vec, row_ok);
-                gf[0] = (float)(int)g.lo.x; gf[1] = (float)(int)g.lo.y; gf[2] = (float)(int)g.hi.x; gf[3] = (float)(int)g.hi.y;
-            }
-            float tgt[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tgt[j] = p.nc_pow2 ? __fmul_rn(gf[j], p.inv_nc) : __fdiv_rn(gf[j], ncf);
-            float u[4];
-            if (FT && p.xs) {
-                const float4 u4 = __ldg(reinterpret_cast<const float4*>(p.xs + col));
-                u[0] = u4.x; u[1] = u4.y; u[2] = u4.z; u[3] = u4.w;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int cx = min(col + j, W - 1);
-                    u[j] = p.xs ? __ldg(p.xs + cx) : mesh_coord(cx, W);
-                }
-            }
-            float o[4];
-            bool any = false;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const Pix qx = pixel_geom<SFH_MODE_BILINEAR>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]),
-                                                             __fmul_rn(u[j], Hm.h[6]), v, Wc_f, Hc_f);
-                const TapVals tv = taps.fetch4(0, qx.x0, qx.y0);
-                o[j] = bilerp(qx, tv);
-                const float d = o[j] - tgt[j];
-                float l, g;
-                if (KMSE || fabsf(d) < 1.0f) { l = d * d; g = d; }
-                else { l = 2.0f * fabsf(d) - 1.0f; g = d > 0.f ? 1.0f : -1.0f; }
-                if (!SFH_PIX_OK(j)) { l = 0.f; g = 0.f; }
-                loss_sum += l;
-                if (__any_sync(0xffffffffu, !tv.uni)) {
-                    g *= gscale;
-                    const float gix = ((tv.b - tv.a) * qx.sy + (tv.d - tv.c) * qx.ny) * g;
-                    const float giy = ((tv.c - tv.a) * qx.ex + (tv.d - tv.b) * qx.wx) * g;
-                    acc.add(qx, gix, giy, halfWc, halfHc, u[j]);
-                    any = true;
-                }
-            }
-            if (p.out_f) {
-                float* op = p.out_f + base + k * kPatchW;
-                if (vec) __stcs((float4*)op, make_float4(o[0], o[1], o[2], o[3]));
-                else
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) op[j] = o[j];
-            }
-            if (any) acc.end_row(v);
-        }
-#undef SFH_PIX_OK
-
-        // ---- 4. the band's sums go to its fixed slot ----
-        float* slot = p.partials + (size_t)unit * kNPart;
-        const float lsum = KMSE ? loss_sum : 0.5f * loss_sum;
-        if (edge_mask) {
-            float vals[16];
-            vals[0] = lsum;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) vals[1 + k] = acc.a[k];
-#pragma unroll
-            for (int k = 10; k < 16; ++k) vals[k] = 0.f;
-            const float tot = warp_reduce16(vals, lane);
-            const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            if (!(lane & 1) && idx < kNPart) slot[idx] = tot;
-        } else {
-            const float tot = warp_sum(lsum);
-            if (lane < kNPart) slot[lane] = lane == 0 ? tot : 0.f;
-        }
-        unit = __shfl_sync(0xffffffffu, next, 0);
-    }
-}
-
 // Second stage of the streaming path: one CTA per sample adds that sample's (tile, warp) slots in
 // fixed order in fp64, then the optional weighting + batch mean + total dtheta (last CTA by ticket).
 constexpr int kFinThreads = 288;                 // 3 float4 columns of a slot x 96 slot lanes
@@ -1482,7 +1221,6 @@ __global__ void __launch_bounds__(kFinThreads) k_train_finalize(const __grid_con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nslots = p.fin_slots;
     asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: the producer grid has completed
-    if (b == 0 && threadIdx.x == 0) p.counters[p.B + 1] = 0;   // k_train_flat's band ticket, for the next launch
     {
         // thread (cq, g): float4 column cq of slots g, g+96, ...; all loads independent (one L2 round trip)
         const int cq = threadIdx.x / 96, g = threadIdx.x % 96;
@@ -1782,42 +1520,6 @@ static int launch_stream(const FusedParams& p, cudaStream_t st) {
     }
 }
 
-template <int FMT, bool KMSE>
-static int launch_flat_fmt(const FusedParams& p, bool ft, int sms, cudaStream_t st) {
-    auto kf = k_train_flat<FMT, true, KMSE>;
-    auto kg = k_train_flat<FMT, false, KMSE>;
-    static int per_sm = 0;
-    if (!per_sm) {
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, kThreads, 0) != cudaSuccess || occ < 1) occ = 1;
-        per_sm = occ;
-    }
-    const int warps_needed = (p.ntiles * p.B + 1) / 2;       // at least two bands per warp
-    int ctas = sms * per_sm;
-    if (ctas > (warps_needed + kWarps - 1) / kWarps) ctas = (warps_needed + kWarps - 1) / kWarps;
-    if (ctas < 1) ctas = 1;
-    if (ft) kf<<<ctas, kThreads, 0, st>>>(p);
-    else    kg<<<ctas, kThreads, 0, st>>>(p);
-    const int rc = (int)cudaGetLastError();
-    return rc ? rc : launch_finalize(p, st);
-}
-
-static int launch_flat(const FusedParams& p, cudaStream_t st) {
-    static const int sms = [] {
-        int dev = 0, n = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        return n;
-    }();
-    const bool ft = p.vec4 && (p.W % kTileW == 0) && (p.H % 8 == 0) && (!p.xs || (((uintptr_t)p.xs & 15u) == 0));
-    const bool mse = p.kind == SFH_LOSS_MSE;
-    switch (p.t.fmt) {
-        case SFH_TMPL_F32: return mse ? launch_flat_fmt<SFH_TMPL_F32, true>(p, ft, sms, st) : launch_flat_fmt<SFH_TMPL_F32, false>(p, ft, sms, st);
-        case SFH_TMPL_Q2:  return mse ? launch_flat_fmt<SFH_TMPL_Q2, true>(p, ft, sms, st) : launch_flat_fmt<SFH_TMPL_Q2, false>(p, ft, sms, st);
-        case SFH_TMPL_Q4:  return mse ? launch_flat_fmt<SFH_TMPL_Q4, true>(p, ft, sms, st) : launch_flat_fmt<SFH_TMPL_Q4, false>(p, ft, sms, st);
-        default: return SFH_E_BADFMT;
-    }
-}
-
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1999,14 +1701,6 @@ int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* a
             q.use_tma = 1;
             return launch_stream(q, (cudaStream_t)stream);
         }
-    }
-    static const bool use_flat = getenv("SFH_FLAT") != nullptr;
-    if (use_flat) {
-        FusedParams q = p;
-        q.rows_per_warp = 1;
-        q.ntiles = ((a->W + kTileW - 1) / kTileW) * ((a->H + 7) / 8);
-        q.fin_slots = q.ntiles;
-        return launch_flat(q, (cudaStream_t)stream);
     }
     p.use_tma = make_gt_map(p) ? 1 : 0;
     // the per-sample / batch reduction runs as a second, programmatically dependent launch: the
