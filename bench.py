@@ -51,6 +51,9 @@ WORKLOADS = {
            1280 * 720 * 4 + 4 * 360 * 640 * 4),
     "c4": (1280, 720, 32, "pitch_v3_nc4", "fwd",
            "C4 pitch v3 HD template bilinear forward 1280x720 batch 32 + POI", 1280 * 720 * 4),
+    "consist": (640, 360, 64, "ncaa_nc4", "consist",
+                "training consistency loss 640x360 batch 64 (SURVEY 8 f-2, train.py:219-223): CE(logits [4,360,640], "
+                "trunc(warp_mask*4)) + dlogits in one launch", 640 * 360 * 4 + 2 * 4 * 360 * 640 * 4),
 }
 L2_BYTES = 126 * 1024 * 1024
 
@@ -135,9 +138,15 @@ def cpu_reference_step(W, H, B, kind, tmpl, poi, seed=0):
     nz = torch.ones(B, pp.shape[1])
     num = nz.sum(1)
     w = torch.ones(B, dtype=torch.float64)
-    logits = torch.randn(B, 4, 360, 640, generator=torch.Generator().manual_seed(3)) if kind == "predict" else None
+    logits = torch.randn(B, 4, 360, 640, generator=torch.Generator().manual_seed(3)) if kind in ("predict", "consist") else None
+    wm = kr.warp(th0, tm, H, W, "bilinear").detach() if kind == "consist" else None
 
     def step():
+        if kind == "consist":                   # train.py:219-223 + the backward to the logits
+            lg = logits.clone().requires_grad_(True)
+            loss = kr.consistency_loss(lg, wm, 4)
+            loss.backward()
+            return float(loss.detach())
         if kind == "train":
             th = th0.clone().requires_grad_(True)
             warp = kr.warp(th, tm, H, W, "bilinear")
@@ -234,6 +243,9 @@ class Workload:
                 s["w"] = torch.ones(B, dtype=torch.float64, device=dev)      # utils/dataset.py:220
             elif self.kind == "predict":
                 s["logits"] = torch.randn(B, 4, 360, 640, device=dev)
+            elif self.kind == "consist":
+                s["logits"] = torch.randn(B, 4, H, W, device=dev)
+                s["wm"] = stb.warp(th)
             self.sets.append(s)
         del stn, stb
 
@@ -244,6 +256,9 @@ class Workload:
                                          1.0, 8.0, True, s["out"])
         if self.kind == "predict":
             return self.stage.predict_tail(s["theta"], s["logits"], True, True, s["out"])
+        if self.kind == "consist":
+            import sfh_b200
+            return sfh_b200.consistency_step(s["logits"], s["wm"], 4, 1.0, True, s["out"])
         r = self.stage.warp(s["theta"])
         if self.kind == "fwd" and self.stage.court_poi is not None and self.W == 1280:
             self.stage.transform_poi(s["theta"])
@@ -374,6 +389,10 @@ def time_e2e(wl, steps, warmup, u8_masks=False):
         elif wl.kind == "predict":
             r = wl.stage.predict_tail(d["theta"], d["logits"], True, True)
             outs = [r["consist_score"], r["poi"]]
+        elif wl.kind == "consist":
+            import sfh_b200
+            r = sfh_b200.consistency_step(d["logits"], d["wm"], 4, 1.0, True)
+            outs = [r["loss"]]
         else:
             r = wl.stage.warp(d["theta"])
             outs = [r.sum()]
