@@ -219,6 +219,27 @@ int sfh_consist_loss_fwd_bwd(const float* warp_mask, const float* logits, int B,
                              float lambda, float* loss_out, float* dlogits,
                              void* workspace, int64_t workspace_bytes, void* stream);
 
+/* GPU post-processing of the predict outputs, done BEFORE the device->host copy:
+ *   src_kind LOGITS:   [B,nc,h,w] fp32 -> class ids by argmax (utils/postprocess.py:7-18 preds_to_masks;
+ *                      argmax(softmax(l)) == argmax(l), first maximum wins)
+ *   src_kind MASK_I32: [B,h,w] int32 as Reconstructor.predict returns it, `.astype(np.uint8)` (predict.py:99)
+ *   src_kind MASK_U8:  [B,h,w] uint8 (the narrow surface of sfh_predict_tail)
+ *   mask_type GRAY: class ids; BIN: (id > 0) * 255 (predict.py:293-297); RGB: id -> colour of
+ *                   utils/postprocess.py:21-58 (nc in {4,7,8}), out [B,oh,ow,3]
+ *   resize: cv2.resize(..., interpolation=cv2.INTER_NEAREST) (predict.py:303-315) through the source
+ *           index tables x_ofs[ow] / y_ofs[oh] (device int32; x_ofs[x] = min(floor(x * w/ow), w-1) evaluated
+ *           in double on the host as cv::resize does); NULL = same size.
+ * out: uint8 [B,oh,ow] (GRAY/BIN) or [B,oh,ow,3] (RGB). */
+#define SFH_POST_SRC_LOGITS   0
+#define SFH_POST_SRC_MASK_I32 1
+#define SFH_POST_SRC_MASK_U8  2
+#define SFH_POST_GRAY 0
+#define SFH_POST_BIN  1
+#define SFH_POST_RGB  2
+int sfh_postprocess(const void* src, int src_kind, int B, int nc, int h, int w,
+                    int mask_type, const int* x_ofs, const int* y_ofs, int oh, int ow,
+                    unsigned char* out, void* stream);
+
 /* Diagnostic: exhaustively compares the kernels' fast correctly-rounded reciprocal with IEEE
  * rcp.rn over every fp32 value with |z| in (1e-8, 1e37) (the range it is used on; the warp path
  * falls back to rcp.rn outside).  *mismatches (device uint64, pre-zeroed) receives the count. */

@@ -256,3 +256,36 @@ def test_consistency_loss_restatement_closed_form():
     assert float(kr.consistency_loss(conf, warp, nc, 3.0)) < 1e-6
     assert float(kr.consistency_loss(conf, warp + 0.2 / nc, nc)) < 1e-6          # still the same class after trunc
     assert float(kr.consistency_loss(conf, warp[:, 0], nc)) < 1e-6                # [B,H,W] accepted
+
+
+def test_postprocess_restatement_matches_cv2_and_golden_tables():
+    """the restated cv2.INTER_NEAREST index rule equals the tables recovered from the real
+    cv2 (tests/golden/cv2_nearest_tables.npz, tools/make_golden_post.py) and, when cv2 is importable,
+    cv2.resize itself; mask_type conversions follow predict.py:288-299 / utils/postprocess.py:21-58."""
+    import os
+    from oracle import postprocess_restated as pr
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cv2_nearest_tables.npz"))
+    n = 0
+    for k in g.files:
+        if k == "cv2_version":
+            continue
+        s, d = map(int, k.split("_"))
+        assert np.array_equal(pr.nearest_table(s, d), g[k]), k
+        n += 1
+    assert n >= 18
+    rng = np.random.default_rng(0)
+    m = rng.integers(0, 4, size=(2, 36, 64)).astype(np.uint8)
+    rgb = pr.onehot_to_image(m, 4)
+    assert rgb.shape == (2, 36, 64, 3) and tuple(rgb[m == 1][0]) == (0, 255, 0) and tuple(rgb[m == 3][0]) == (0, 0, 255)
+    assert not rgb[m == 0].any()
+    logits = torch.randn(2, 4, 36, 64)
+    assert np.array_equal(pr.preds_to_masks(logits, 4), logits.argmax(1).numpy().astype(np.uint8))
+    b = pr.postprocess(torch.from_numpy(m.astype(np.int32)), "mask", "bin", (100, 50), 4)
+    assert b.shape == (2, 50, 100) and set(np.unique(b)) <= {0, 255}
+    try:
+        import cv2
+    except ImportError:
+        return
+    for (ow, oh) in [(128, 72), (100, 50), (64, 36), (31, 17), (200, 111)]:
+        for arr in (m[0], rgb[0]):
+            assert np.array_equal(pr.resize_nearest(arr, (ow, oh)), cv2.resize(arr, (ow, oh), interpolation=cv2.INTER_NEAREST))

@@ -604,6 +604,49 @@ def test_consistency_loss_on_the_warp_stage_output():
         sfh_b200.consistency_step(logits.cpu(), wm, 4)
 
 
+@pytest.mark.parametrize("kind", ["logits", "mask_i32", "mask_u8"])
+@pytest.mark.parametrize("mask_type", ["gray", "bin", "rgb"])
+@pytest.mark.parametrize("size,out_size", [((640, 360), None), ((640, 360), (1280, 720)), ((1280, 720), (640, 360)),
+                                           ((200, 77), (333, 130)), ((130, 50), (64, 36))])
+def test_postprocess_matches_reference_cpu_path(kind, mask_type, size, out_size):
+    """argmax / uint8 cast / mask_type / cv2 nearest resize on the device == the reference's
+    CPU sequence (predict.py:99,288-315, utils/postprocess.py), bit for bit."""
+    from oracle import postprocess_restated as pr
+    W, H = size
+    B, nc = 3, 4
+    g = torch.Generator().manual_seed(W + (out_size or (0, 0))[0])
+    if kind == "logits":
+        src = torch.randn(B, nc, H, W, generator=g)
+        src[0, :, :4, :8] = 0.5                                    # ties: the first class wins in both
+        src[1, 1:3, 5, 7] = src[1, 1:3, 5, 7].max()
+        ref = pr.postprocess(src, "logits", mask_type, out_size, nc)
+    else:
+        src = torch.randint(0, nc, (B, H, W), generator=g).to(torch.int32 if kind == "mask_i32" else torch.uint8)
+        ref = pr.postprocess(src, "mask", mask_type, out_size, nc)
+    got = sfh_b200.postprocess_masks(src.to(DEV), mask_type, out_size, nc)
+    assert got.dtype == torch.uint8 and tuple(got.shape) == ref.shape
+    assert np.array_equal(got.cpu().numpy(), ref)
+
+
+def test_postprocess_after_predict_tail_and_errors():
+    tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (1280, 720), 4, 1)
+    st = mk_stage(tmpl.to(DEV), poi.to(DEV), (1280, 720), 4, warp_with_nearest=True)
+    th = _thetas("b", 2, 11).to(DEV)
+    r = st.predict_tail(th, None, False, False)
+    from oracle import postprocess_restated as pr
+    for mt in ("gray", "rgb"):
+        got = sfh_b200.postprocess_masks(r["warp_mask"], mt, (1920, 1080), 4)
+        assert np.array_equal(got.cpu().numpy(), pr.postprocess(r["warp_mask"].cpu(), "mask", mt, (1920, 1080), 4))
+    with pytest.raises(NotImplementedError):
+        sfh_b200.postprocess_masks(r["warp_mask"], "rgb", None, 5)
+    with pytest.raises(NotImplementedError):
+        sfh_b200.postprocess_masks(r["warp_mask"], "hsv")
+    with pytest.raises(TypeError):
+        sfh_b200.postprocess_masks(r["warp_mask"].cpu())
+    with pytest.raises(TypeError):
+        sfh_b200.postprocess_masks(r["warp_mask"].float())
+
+
 # ---------------------------------------------------------------------- API / error conventions
 def test_error_conventions_and_state_dict():
     tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 2)

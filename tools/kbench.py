@@ -78,6 +78,14 @@ for (W, H, B) in cfgs:
                 s_["cons"] = {}
             run(f"consist_ce+dlogits_{W}x{H}_B{B}", lambda i: sfh_b200.consistency_step(S(i)["logits"], S(i)["wm"], 4, 1.0, True, S(i)["cons"]), px * 4 + 2 * B * 4 * H * W * 4)
             run(f"consist_ce_fwd_only_{W}x{H}_B{B}", lambda i: sfh_b200.consistency_step(S(i)["logits"], S(i)["wm"], 4, 1.0, False, S(i)["cons"]), px * 4 + B * 4 * H * W * 4)
+        for s_ in sets:
+            s_["mi"] = stn.predict_tail(s_["th"], None, False, False)["warp_mask"]
+            s_["post"] = {}
+        def post(i, src, mt, osz):
+            S(i)["post"][(mt, osz)] = sfh_b200.postprocess_masks(S(i)[src], mt, osz, 4, S(i)["post"].get((mt, osz)))
+        run(f"post_argmax_gray_{W}x{H}_B{B}", lambda i: post(i, "logits", "gray", None), B * 360 * 640 * 17)
+        run(f"post_argmax_rgb_x2_{W}x{H}_B{B}", lambda i: post(i, "logits", "rgb", (1280, 720)), B * 360 * 640 * 16 + B * 1280 * 720 * 3)
+        run(f"post_mask_i32_rgb_{W}x{H}_B{B}", lambda i: post(i, "mi", "rgb", None), px * 7)
         go = torch.randn(B, 1, H, W, device=dev)
         thg = S(0)["th"]
         def bwd(i):
