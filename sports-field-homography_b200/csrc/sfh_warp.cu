@@ -306,15 +306,17 @@ __device__ __forceinline__ void tl_stamp(int cta, int phase) {
 #define SFH_TLS(w, phase)
 #endif
 
-// (sample, tile row) of this CTA.  CTAs are dispatched x-fastest, then y, then z; with `short_last`
-// (z, y) is remapped so that every sample's full-height tile rows come first and the short bottom
-// rows of all samples form the end of the grid (a shorter tail).
-__device__ __forceinline__ void block_tile(int short_last, int& b, int& ty) {
+// (sample, tile row) of this CTA.  CTAs are dispatched x-fastest, then y, then z.  With `short_last`
+// (the image height is not a multiple of the tile height) grid.y only spans the full-height tile rows
+// and the short bottom row of every sample is appended as extra z-slices (slice B + s/full, row
+// s % full holds sample s), so the short tiles form the end of the grid — a shorter tail — without
+// any division.  b < 0: an unused slot of the last extra slice.
+__device__ __forceinline__ void block_tile(int short_last, int B, int& b, int& ty) {
     b = blockIdx.z; ty = blockIdx.y;
-    if (short_last) {
-        const int full = (int)gridDim.y - 1, L = (int)(blockIdx.z * gridDim.y + blockIdx.y), nfull = full * (int)gridDim.z;
-        if (L < nfull) { b = L / full; ty = L - b * full; }
-        else { b = L - nfull; ty = full; }
+    if (short_last && b >= B) {
+        b = (b - B) * (int)gridDim.y + ty;
+        ty = (int)gridDim.y;
+        if (b >= B) b = -1;
     }
 }
 
@@ -335,7 +337,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     constexpr bool kMse = (EPI != kEpiLoss) || (MODE == SFH_LOSS_MSE);
     int b, ty;
     const int tx = blockIdx.x;
-    block_tile(p.short_last, b, ty);
+    block_tile(p.short_last, p.B, b, ty);
+    if (b < 0) return;
     const int tile = ty * gridDim.x + tx;
     const int H = p.H, W = p.W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -700,7 +703,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     {
         int sl = p.short_last;
         asm volatile("" : "+r"(sl));
-        block_tile(sl, bE, tyE);
+        block_tile(sl, p.B, bE, tyE);
     }
     const int tileE = tyE * gridDim.x + tx;
     if (EPI == kEpiLoss && !kMse) loss_sum *= 0.5f;
@@ -1448,6 +1451,11 @@ static int launch_fused(const FusedParams& p_in, cudaStream_t st) {
     dim3 grid(tiles_x, p.ntiles / tiles_x, p.B);
     static const bool no_remap = getenv("SFH_NO_REMAP") != nullptr;
     p.short_last = (!no_remap && grid.y > 1 && (p.H % (8 * p.rows_per_warp)) != 0) ? 1 : 0;
+    if (p.short_last) {                        // full rows in y, the short rows of all samples as extra z-slices
+        grid.y -= 1;
+        grid.z = p.B + (p.B + grid.y - 1) / grid.y;
+        if (grid.z > 65535) { grid.y += 1; grid.z = p.B; p.short_last = 0; }
+    }
     const bool ft = p.vec4 && (p.W % kTileW == 0) && (p.H % 8 == 0) &&
                     (!p.xs || (((uintptr_t)p.xs & 15u) == 0));
     const size_t dyn = !p.use_tma ? 0

@@ -283,6 +283,18 @@ class STNWarpStage(torch.nn.Module):
             ret["poi"] = poi
         return ret
 
+    def render_masks(self, theta: torch.Tensor, mask_type: str = "rgb", out_size=None,
+                     out: Optional[dict] = None) -> torch.Tensor:
+        """The per-frame mask rendering of viz_preds.py:119-136 (first consumer), batched:
+        ``warper(court_img, theta) * mask_classes`` -> uint8 -> ``onehot_to_image`` / bin / gray ->
+        optional cv2 nearest resize, two launches, uint8 result on the device.  The stage must have been
+        built with ``warp_with_nearest=True`` to reproduce viz_preds' ``mode='nearest'`` warper."""
+        from .post import postprocess_masks
+        out = {} if out is None else out
+        r = self.predict_tail(theta, None, False, False, out, torch.uint8)
+        out["rendered"] = postprocess_masks(r["warp_mask"], mask_type, out_size, self.mask_classes, out.get("rendered"))
+        return out["rendered"]
+
     def _check_train_args(self, theta, gt_masks, rec_loss, gt_poi, nonzeros, num_nonzero, weights):
         if self.mode != "bilinear":
             raise ValueError("train_tail needs a bilinear warper (nearest has no gradient)")

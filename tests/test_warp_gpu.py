@@ -647,6 +647,19 @@ def test_postprocess_after_predict_tail_and_errors():
         sfh_b200.postprocess_masks(r["warp_mask"].float())
 
 
+def test_render_masks_matches_viz_preds_sequence():
+    """SURVEY §8 f-4 (viz_preds.py:119-136): nearest warp * nc -> IntTensor -> uint8 -> onehot_to_image."""
+    from oracle import postprocess_restated as pr
+    tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 1)
+    st = mk_stage(tmpl.to(DEV), poi.to(DEV), (640, 360), 4, warp_with_nearest=True)
+    th = _thetas("b", 5, 21)
+    mask = (co.warp_fwd(th.numpy(), tmpl.numpy(), 360, 640, "nearest")[:, 0] * 4).astype(np.int32).astype(np.uint8)
+    got = st.render_masks(th.to(DEV), "rgb")
+    assert np.array_equal(got.cpu().numpy(), pr.onehot_to_image(mask, 4))
+    got2 = st.render_masks(th.to(DEV), "gray", (1280, 720))
+    assert np.array_equal(got2.cpu().numpy(), np.stack([pr.resize_nearest(m, (1280, 720)) for m in mask]))
+
+
 # ---------------------------------------------------------------------- API / error conventions
 def test_error_conventions_and_state_dict():
     tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 2)
