@@ -265,8 +265,9 @@ class Workload:
         return r
 
     def launches_per_step(self):
-        # train: k_fused + k_train_finalize (programmatic dependent launch); C4: warp + POI kernel
-        return 2 if (self.kind == "train" or (self.kind == "fwd" and self.W == 1280)) else 1
+        # train / predict: k_fused + k_train_finalize / k_score_finalize (programmatic dependent launch);
+        # C4: warp + POI kernel
+        return 2 if (self.kind in ("train", "predict") or (self.kind == "fwd" and self.W == 1280)) else 1
 
 
 def time_workload(wl, steps, warmup, use_graph, dist_vec=None):

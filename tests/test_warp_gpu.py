@@ -537,7 +537,13 @@ for (W, H, B, kind) in [(640, 360, 9, 'MSE'), (200, 77, 5, 'SmoothL1'), (1280, 7
     for rep in range(2):                       # second call: the workspace is reused
         r = st.train_step(th, gt, w, kind, gp, nz, nz.sum(1), 1.0, 8.0, True, {})
     torch.cuda.synchronize()
+    lg = torch.randn(B, 4, H // 2 if H %% 2 == 0 and W %% 2 == 0 else H, W // 2 if H %% 2 == 0 and W %% 2 == 0 else W,
+                     generator=torch.Generator().manual_seed(9)).to(dev)
+    for rep in range(2):
+        pr_ = stn.predict_tail(th, lg, True, True, {})
+    torch.cuda.synchronize()
     out['%%dx%%d' %% (W, H)] = dict(loss=float(r['loss']), mask=float(r['warp_mask'].double().sum()),
+                                score=pr_['consist_score'].double().cpu().tolist(), pmask=float(pr_['warp_mask'].double().sum()),
                                 mask_sq=float((r['warp_mask'].double() ** 2).sum()),
                                 rec=r['rec_per_sample'].double().cpu().tolist(), dth=r['dtheta'].double().flatten().cpu().tolist())
 print('RESULT' + json.dumps(out))
@@ -555,6 +561,8 @@ print('RESULT' + json.dumps(out))
             assert a["mask"] == b["mask"] and a["mask_sq"] == b["mask_sq"], (name, cfg)
             assert abs(a["loss"] - b["loss"]) <= 1e-6 * abs(a["loss"]), (name, cfg, a["loss"], b["loss"])
             np.testing.assert_allclose(b["rec"], a["rec"], rtol=1e-6, atol=1e-9)
+            assert a["pmask"] == b["pmask"]
+            np.testing.assert_allclose(b["score"], a["score"], rtol=1e-6)     # predict tail: score by k_score_finalize vs tickets
             scale = max(abs(x) for x in a["dth"])
             np.testing.assert_allclose(b["dth"], a["dth"], rtol=0, atol=1e-5 * scale)
 
