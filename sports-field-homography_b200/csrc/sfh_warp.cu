@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     const bool tma = (EPI == kEpiLoss || EPI == kEpiPredict) && p.use_tma;
 
     SFH_TL(0);
-    if (EPI == kEpiLoss || EPI == kEpiPredict) asm volatile("griddepcontrol.launch_dependents;");   // lets the finalize grid become resident early
+    if (EPI != kEpiStore) asm volatile("griddepcontrol.launch_dependents;");   // lets the finalize grid become resident early
     if (tma && threadIdx.x == 0) {
         // the tile's streaming input is requested before anything else so that it arrives behind
         // the whole prologue (evict-first in L2: it is read exactly once)
@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         for (int w = 0; w < kWarps; ++w) s += s_red[w][threadIdx.x];
         __stcg(p.partials + ((size_t)bE * p.ntiles + tileE) * kNPart + threadIdx.x, s);
     }
-    if ((EPI == kEpiLoss || EPI == kEpiPredict) && p.split_finalize) return;   // reduced by k_train_finalize / k_score_finalize
+    if (EPI != kEpiStore && p.split_finalize) return;   // reduced by k_train_finalize / k_comp_finalize (next launch)
     __syncthreads();
     SFH_TL(5);
     if (threadIdx.x == 0) s_last = (ticket_release(p.counters + bE) == p.ntiles - 1);
@@ -1469,24 +1469,28 @@ static int launch_fused(const FusedParams& p_in, cudaStream_t st) {
     }
 }
 
-// Second launch of the predict tail: consist_score[b] = sum of the sample's CE partials (component 10)
-// in fixed order in fp64, divided by the number of logits pixels (models/reconstructor.py:238-239).
-__global__ void __launch_bounds__(128) k_score_finalize(const __grid_constant__ FusedParams p) {
-    __shared__ double s_w[4];
+// Second launch of the predict tail and of the generic backward: components [k0, k0+nk) of every sample's
+// partials are added in fixed order in fp64 (one warp per component, lanes stride the slots) and written
+// as out[b * nk + (k - k0)] = sum * scale.
+//   predict:  k0 = 10, nk = 1, scale = 1 / (h*w)  -> consist_score[b]   (models/reconstructor.py:238-239)
+//   backward: k0 = 1,  nk = 9, scale = 1          -> dtheta[b]          (autograd of HomographyWarper)
+__global__ void __launch_bounds__(128) k_comp_finalize(const __grid_constant__ FusedParams p, int k0, int nk,
+                                                       float* out, double scale) {
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const float* base = p.partials + (size_t)b * p.fin_slots * kNPart + 10;
-    double s = 0.0;
-    for (int t = threadIdx.x; t < p.fin_slots; t += 128) s += (double)__ldcg(base + (size_t)t * kNPart);
-    s = warp_sum(s);
-    if (lane == 0) s_w[warp] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) p.score[b] = (float)(((s_w[0] + s_w[1]) + (s_w[2] + s_w[3])) / ((double)p.lh * (double)p.lw));
+    for (int c = warp; c < nk; c += 4) {
+        const float* base = p.partials + (size_t)b * p.fin_slots * kNPart + k0 + c;
+        double s = 0.0;
+        for (int t = lane; t < p.fin_slots; t += 32) s += (double)__ldcg(base + (size_t)t * kNPart);
+        s = warp_sum(s);
+        if (lane == 0) out[(size_t)b * nk + c] = (float)(s * scale);
+    }
 }
 
 // k_train_finalize as a programmatically dependent launch: it may become resident while the
 // producer grid drains and waits in griddepcontrol.wait, which hides its launch latency.
-static int launch_finalize(const FusedParams& p, cudaStream_t st, bool score_only = false) {
+// comps: 0 = training tail (k_train_finalize), 1 = predict score, 9 = backward dtheta (k_comp_finalize)
+static int launch_finalize(const FusedParams& p, cudaStream_t st, int comps = 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.B); cfg.blockDim = dim3(kFinThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1495,9 +1499,10 @@ static int launch_finalize(const FusedParams& p, cudaStream_t st, bool score_onl
     cfg.attrs = attr; cfg.numAttrs = 1;
     static const bool no_pdl = getenv("SFH_NO_PDL") != nullptr;
     if (no_pdl) cfg.numAttrs = 0;
-    if (score_only) {
+    if (comps) {
         cfg.blockDim = dim3(128);
-        return (int)cudaLaunchKernelEx(&cfg, k_score_finalize, p);
+        if (comps == 1) return (int)cudaLaunchKernelEx(&cfg, k_comp_finalize, p, 10, 1, p.score, 1.0 / ((double)p.lh * (double)p.lw));
+        return (int)cudaLaunchKernelEx(&cfg, k_comp_finalize, p, 1, 9, p.dtheta, 1.0);
     }
     return (int)cudaLaunchKernelEx(&cfg, k_train_finalize, p);
 }
@@ -1677,7 +1682,12 @@ int sfh_warp_bwd(const float* theta, const sfh_template* tmpl, const float* xs, 
     if ((rc = setup_ws(p, workspace, workspace_bytes))) return rc;
     p.grad_out = grad_out; p.dtheta = dtheta;
     p.vec4 = (W % 4 == 0) && aligned16(grad_out);
-    return launch_fused<SFH_MODE_BILINEAR, kEpiBwd>(p, (cudaStream_t)stream);
+    static const bool one_launch = getenv("SFH_ONE_LAUNCH") != nullptr;
+    p.split_finalize = one_launch ? 0 : 1;
+    p.fin_slots = p.ntiles;
+    rc = launch_fused<SFH_MODE_BILINEAR, kEpiBwd>(p, (cudaStream_t)stream);
+    if (rc || !p.split_finalize) return rc;
+    return launch_finalize(p, (cudaStream_t)stream, 9);
 }
 
 int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* a, void* stream) {
@@ -1774,7 +1784,7 @@ int sfh_predict_tail(const sfh_template* tmpl, const sfh_predict_tail_args* a, v
     else if (a->mode == SFH_MODE_BILINEAR) rc = launch_fused<SFH_MODE_BILINEAR, kEpiPredict>(p, st);
     else return SFH_E_BADMODE;
     if (rc) return rc;
-    if (split && (rc = launch_finalize(p, st, true))) return rc;
+    if (split && (rc = launch_finalize(p, st, 1))) return rc;
     if (a->score && p.ratio == 0) {
         k_consistency_generic<<<a->B, kThreads, 0, st>>>(p.out_i, p.out_u8, a->logits, a->nc, a->H, a->W, a->h, a->w, a->score);
         rc = (int)cudaGetLastError();

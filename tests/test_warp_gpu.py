@@ -542,7 +542,11 @@ for (W, H, B, kind) in [(640, 360, 9, 'MSE'), (200, 77, 5, 'SmoothL1'), (1280, 7
     for rep in range(2):
         pr_ = stn.predict_tail(th, lg, True, True, {})
     torch.cuda.synchronize()
+    tg = th.clone().requires_grad_(True)
+    go = torch.randn(B, 1, H, W, generator=torch.Generator().manual_seed(4)).to(dev)
+    st.warper(st.court_img, tg).backward(go)
     out['%%dx%%d' %% (W, H)] = dict(loss=float(r['loss']), mask=float(r['warp_mask'].double().sum()),
+                                gbwd=tg.grad.double().flatten().cpu().tolist(),
                                 score=pr_['consist_score'].double().cpu().tolist(), pmask=float(pr_['warp_mask'].double().sum()),
                                 mask_sq=float((r['warp_mask'].double() ** 2).sum()),
                                 rec=r['rec_per_sample'].double().cpu().tolist(), dth=r['dtheta'].double().flatten().cpu().tolist())
@@ -562,6 +566,7 @@ print('RESULT' + json.dumps(out))
             assert abs(a["loss"] - b["loss"]) <= 1e-6 * abs(a["loss"]), (name, cfg, a["loss"], b["loss"])
             np.testing.assert_allclose(b["rec"], a["rec"], rtol=1e-6, atol=1e-9)
             assert a["pmask"] == b["pmask"]
+            np.testing.assert_allclose(b["gbwd"], a["gbwd"], rtol=0, atol=1e-5 * max(abs(x) for x in a["gbwd"]))   # generic backward
             np.testing.assert_allclose(b["score"], a["score"], rtol=1e-6)     # predict tail: score by k_score_finalize vs tickets
             scale = max(abs(x) for x in a["dth"])
             np.testing.assert_allclose(b["dth"], a["dth"], rtol=0, atol=1e-5 * scale)
