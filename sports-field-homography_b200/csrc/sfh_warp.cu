@@ -249,6 +249,9 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+#ifndef SFH_PIPE_PIX
+#define SFH_PIPE_PIX 1
+#endif
 #ifndef SFH_MINCTAS_HEAVY
 #define SFH_MINCTAS_HEAVY 3   // loss / backward epilogues: <= 80 registers
 #endif
@@ -613,11 +616,33 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             // only o[j] crosses iterations, which keeps the live state small enough for 4 CTAs/SM
             float o[4];
             bool any = false;
+            // packed templates: the geometry and the packed-entry load of pixel j+1 are issued before
+            // pixel j's value / loss / chain rule, so one load is always in flight (SFH_PIPE_PIX)
+            constexpr bool kPipe = (FMT != SFH_TMPL_F32) && (SFH_PIPE_PIX != 0);
+            Pix qn;
+            unsigned vn = 0u;
+            if (kPipe) {
+                qn = pixel_geom<SMODE>(Hm, __fmul_rn(u[0], Hm.h[0]), __fmul_rn(u[0], Hm.h[3]), __fmul_rn(u[0], Hm.h[6]), v, Wc_f, Hc_f);
+                vn = taps.quad(qn.x0, qn.y0);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const Pix q = pixel_geom<SMODE>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]),
-                                               __fmul_rn(u[j], Hm.h[6]), v, Wc_f, Hc_f);
-                const TapVals t = taps.fetch4(0, q.x0, q.y0);
+                Pix q;
+                TapVals t;
+                if (kPipe) {
+                    q = qn;
+                    const unsigned vq = vn;
+                    if (j < 3) {
+                        qn = pixel_geom<SMODE>(Hm, __fmul_rn(u[j + 1], Hm.h[0]), __fmul_rn(u[j + 1], Hm.h[3]),
+                                               __fmul_rn(u[j + 1], Hm.h[6]), v, Wc_f, Hc_f);
+                        vn = taps.quad(qn.x0, qn.y0);
+                    }
+                    t = taps.decode(vq);
+                } else {
+                    q = pixel_geom<SMODE>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]),
+                                          __fmul_rn(u[j], Hm.h[6]), v, Wc_f, Hc_f);
+                    t = taps.fetch4(0, q.x0, q.y0);
+                }
                 o[j] = bilerp(q, t);
                 const float d = o[j] - tgt[j];
                 float l, g;
