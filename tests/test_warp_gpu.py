@@ -673,6 +673,63 @@ def test_render_masks_matches_viz_preds_sequence():
     assert np.array_equal(got2.cpu().numpy(), np.stack([pr.resize_nearest(m, (1280, 720)) for m in mask]))
 
 
+def _guarded(shape, dtype, fill):
+    """A tensor that sits in the middle of a sentinel-filled buffer: (view, check) where check() asserts that
+    nothing outside the view was written (stand-in for compute-sanitizer, which this pool does not offer)."""
+    n = int(np.prod(shape)) if len(shape) else 1
+    pad = 4096
+    buf = torch.full((n + 2 * pad,), fill, dtype=dtype, device=DEV)
+    view = buf[pad:pad + n].view(shape)
+
+    def check():
+        assert bool((buf[:pad] == fill).all()) and bool((buf[pad + n:] == fill).all()), "write outside the output tensor"
+    return view, check
+
+
+@pytest.mark.parametrize("W,H,B", [(200, 77, 5), (130, 50, 2), (640, 360, 3), (1276, 716, 2)])
+def test_no_writes_outside_outputs_at_ragged_sizes(W, H, B):
+    tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (1280, 720) if W > 640 else (640, 360), 4, 1)
+    st = mk_stage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, exact=False)
+    stn = mk_stage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, warp_with_nearest=True, exact=False)
+    th = _thetas("b", B, 5).to(DEV)
+    N = poi.shape[1]
+    gt = torch.randint(0, 4, (B, H, W), device=DEV)
+    gp = torch.rand(B, N, 2, device=DEV)
+    nz = torch.ones(B, N, device=DEV)
+    checks = []
+
+    def g(shape, dtype, fill):
+        v, c = _guarded(shape, dtype, fill)
+        checks.append(c)
+        return v
+    out = {"warp_mask": g((B, H, W), torch.float32, 7.0), "loss": g((), torch.float32, 7.0),
+           "dtheta": g((B, 9), torch.float32, 7.0), "poi": g((B, N, 2), torch.float32, 7.0),
+           "Lb": g((B,), torch.float32, 7.0), "J": g((B, 9), torch.float32, 7.0),
+           "Rb": g((B,), torch.float32, 7.0), "K": g((B, 9), torch.float32, 7.0)}
+    r = st.train_step(th, gt, torch.ones(B, dtype=torch.float64, device=DEV), "MSE", gp, nz, nz.sum(1), 1.0, 8.0, True, out)
+    assert r["warp_mask"].data_ptr() == out["warp_mask"].data_ptr()
+    for dt, fill in ((torch.int32, 77), (torch.uint8, 77)):
+        po = {"warp_mask": g((B, H, W), dt, fill), "consist_score": g((B,), torch.float32, 7.0), "poi": g((B, N, 2), torch.float32, 7.0)}
+        lg = torch.randn(B, 4, H // 2, W // 2, device=DEV)
+        rp = stn.predict_tail(th, lg, True, True, po, dt)
+        assert rp["warp_mask"].data_ptr() == po["warp_mask"].data_ptr()
+    lg = torch.randn(B, 4, H, W, device=DEV)
+    co_ = {"dlogits": g((B, 4, H, W), torch.float32, 7.0), "loss": g((), torch.float32, 7.0)}
+    rc = sfh_b200.consistency_step(lg, r["warp_mask"], 4, 1.0, True, co_)
+    assert rc["dlogits"].data_ptr() == co_["dlogits"].data_ptr()
+    for mt, ch in (("gray", ()), ("rgb", (3,))):
+        for osz in (None, (W + 37, H + 11), (W // 2 + 1, H // 2)):
+            ow, oh = (W, H) if osz is None else osz
+            o = g((B, oh, ow) + ch, torch.uint8, 99)
+            got = sfh_b200.postprocess_masks(lg, mt, osz, 4, o)
+            assert got.data_ptr() == o.data_ptr()
+    tg = th.clone().requires_grad_(True)
+    st.warper(st.court_img, tg).sum().backward()
+    torch.cuda.synchronize()
+    for c in checks:
+        c()
+
+
 # ---------------------------------------------------------------------- API / error conventions
 def test_error_conventions_and_state_dict():
     tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 2)
