@@ -1605,7 +1605,7 @@ static bool make_gt_map(FusedParams& p) {
     const cuuint32_t box[3] = {(cuuint32_t)kTileW, (cuuint32_t)(8 * p.rows_per_warp), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(&p.gt_map, p.gt8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_INT64, 3, (void*)base, dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
