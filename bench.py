@@ -473,6 +473,12 @@ def main_ours(args):
                 traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
         frames = wl.B * world
         step_bytes = wl.B * wl.bytes_per_frame
+        # duration of the step's launches: the timed region itself (K back-to-back steps between one CUDA
+        # event pair on the launching stream => average duration per step, kernels + finalize + gaps, an upper
+        # bound on the dominant kernel's own time).  The isolated per-launch event pairs (2 us timer
+        # granularity, eager launch gaps inside the pair) are reported next to it.
+        kern_us_isolated = kern_us
+        kern_us = min(ms * 1e3, kern_us_isolated)   # both bound the kernel time from above
         achieved = step_bytes / (kern_us * 1e-6) / 1e9
         line = {
             "metric": "warped frames/s (fwd+bwd)", "value": frames / (ms * 1e-3), "unit": "frames/s",
@@ -491,7 +497,9 @@ def main_ours(args):
             "gpu_launches": args.steps * wl.launches_per_step(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "sfh::k_fused",
-                         "kernel_us": kern_us, "algorithmic_bytes_per_launch": step_bytes,
+                         "kernel_us": kern_us, "kernel_us_isolated_event_pairs": kern_us_isolated,
+                         "duration_source": "min(timed region / steps, isolated per-launch event pairs): CUDA events on the launching stream",
+                         "algorithmic_bytes_per_launch": step_bytes,
                          "bytes_per_frame": wl.bytes_per_frame},
         }
         if world == 1 and not args.no_extra and wl.kind == "train":
@@ -530,7 +538,9 @@ def main_ours(args):
                     w2 = Workload(name, dev, seed=7)
                     m2, k2, md2, _ = time_workload(w2, 200, 10, not args.no_graph)
                     sb = w2.B * w2.bytes_per_frame
+                    k2i, k2 = k2, min(k2, m2 * 1e3)
                     extra[name] = {"frames_per_s": w2.B / (m2 * 1e-3), "ms_per_step": m2, "kernel_us": k2,
+                                   "kernel_us_isolated_event_pairs": k2i,
                                    "achieved_GBps": sb / (k2 * 1e-6) / 1e9, "frac_of_hbm_peak": sb / (k2 * 1e-6) / 1e9 / peak,
                                    "launch": md2, "workload": w2.desc}
                     del w2
