@@ -354,6 +354,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
 
     SFH_TL(0);
     if (EPI != kEpiStore) asm volatile("griddepcontrol.launch_dependents;");   // lets the finalize grid become resident early
+    Taps<FMT> taps;
+    taps.build_tables(p.t, s_tab);           // from kernel parameters only: may run before the dependency wait
+    // Programmatic dependent launch on the consumer side too: this grid may become resident while the
+    // previous kernel of the stream (e.g. the previous step's finalize) is still running; everything
+    // that touches global memory comes after this wait (no-op when launched without the attribute).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tma && threadIdx.x == 0) {
         // the tile's streaming input is requested before anything else so that it arrives behind
         // the whole prologue (evict-first in L2: it is read exactly once)
@@ -367,8 +373,6 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             tma_load_4d(s_dyn, &p.gt_map, tx * (kTileW / 2), band0 >> 1, 0, b, &s_bar, pol);
         }
     }
-    Taps<FMT> taps;
-    taps.build_tables(p.t, s_tab);
     if ((EPI == kEpiLoss || EPI == kEpiPredict) && tile == 0 && p.poi.court_poi)
         poi_block(p.poi, b);                 // first warp: the 52/33 court points in fp64
     Homog Hm;
@@ -1248,6 +1252,7 @@ __global__ void __launch_bounds__(kFinThreads) k_train_finalize(const __grid_con
     const int b = blockIdx.x, H = p.H, W = p.W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nslots = p.fin_slots;
+    asm volatile("griddepcontrol.launch_dependents;");   // the next kernel of the stream may become resident (it waits itself)
     asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: the producer grid has completed
     {
         // thread (cq, g): float4 column cq of slots g, g+96, ...; all loads independent (one L2 round trip)
@@ -1463,9 +1468,14 @@ static int launch_fmt(const FusedParams& p, dim3 grid, size_t dyn, bool ft, cuda
             raised = true;
         }
     }
-    if (ft) kf<<<grid, kThreads, dyn, st>>>(p);
-    else    kg<<<grid, kThreads, dyn, st>>>(p);
-    return (int)cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = dyn; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("SFH_NO_PDL_MAIN") != nullptr;
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    return (int)(ft ? cudaLaunchKernelEx(&cfg, kf, p) : cudaLaunchKernelEx(&cfg, kg, p));
 }
 
 template <int MODE, int EPI>
@@ -1502,6 +1512,7 @@ static int launch_fused(const FusedParams& p_in, cudaStream_t st) {
 __global__ void __launch_bounds__(128) k_comp_finalize(const __grid_constant__ FusedParams p, int k0, int nk,
                                                        float* out, double scale) {
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int c = warp; c < nk; c += 4) {
         const float* base = p.partials + (size_t)b * p.fin_slots * kNPart + k0 + c;
