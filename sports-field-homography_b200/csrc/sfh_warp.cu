@@ -1254,6 +1254,24 @@ __global__ void __launch_bounds__(kFinThreads) k_train_finalize(const __grid_con
     const int nslots = p.fin_slots;
     asm volatile("griddepcontrol.launch_dependents;");   // the next kernel of the stream may become resident (it waits itself)
     asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: the producer grid has completed
+    // warp 0 requests what the combine stage needs (weights, dR_b/dtheta, R_b) together with the partials,
+    // so the tail of this kernel is one L2 round trip shorter
+    const bool rep = p.poi.gt_poi != nullptr;
+    double w_eff = 1.0, Kk = 0.0, Rv = 0.0;
+    if (p.loss_out && warp == 0) {
+        if (p.weights) {
+            if (p.w_outer) {            // [B]*[B,1] -> [B,B] broadcast quirk: every sample sees mean(w)
+                double sw = 0.0;
+                for (int i = lane; i < p.B; i += 32)
+                    sw += p.w_f64 ? ((const double*)p.weights)[i] : (double)((const float*)p.weights)[i];
+                w_eff = warp_sum(sw) / (double)p.B;
+            } else {
+                w_eff = p.w_f64 ? ((const double*)p.weights)[b] : (double)((const float*)p.weights)[b];
+            }
+        }
+        if (rep && lane < 9) Kk = (double)__ldcg(p.poi.K + 9 * b + lane);
+        if (rep && lane == 0) Rv = (double)__ldcg(p.poi.Rb + b);
+    }
     {
         // thread (cq, g): float4 column cq of slots g, g+96, ...; all loads independent (one L2 round trip)
         const int cq = threadIdx.x / 96, g = threadIdx.x % 96;
@@ -1279,26 +1297,10 @@ __global__ void __launch_bounds__(kFinThreads) k_train_finalize(const __grid_con
     __syncthreads();
     if (warp == 0) {
         const int B = p.B;
-        double w_eff = 1.0;
-        if (p.weights) {
-            if (p.w_outer) {
-                double sw = 0.0;
-                for (int i = lane; i < B; i += 32)
-                    sw += p.w_f64 ? ((const double*)p.weights)[i] : (double)((const float*)p.weights)[i];
-                w_eff = warp_sum(sw) / (double)B;
-            } else {
-                w_eff = p.w_f64 ? ((const double*)p.weights)[b] : (double)((const float*)p.weights)[b];
-            }
-        }
-        const bool rep = p.poi.gt_poi != nullptr;
         const double cr = (double)p.rec_lambda * w_eff, cp = (double)p.reproj_lambda;
-        if (lane < 9) {
-            const double Kk = rep ? (double)p.poi.K[9 * b + lane] : 0.0;
-            p.dtheta_total[9 * b + lane] = (float)((cr * s_out[1 + lane] + cp * Kk) / (double)B);
-        }
+        if (lane < 9) p.dtheta_total[9 * b + lane] = (float)((cr * s_out[1 + lane] + cp * Kk) / (double)B);
         int last2 = 0;
         if (lane == 0) {
-            const double Rv = rep ? (double)p.poi.Rb[b] : 0.0;
             __stcg(p.contrib + b, cr * s_out[0] + cp * Rv);
             last2 = (ticket_release(p.counters + B) == B - 1);
         }
