@@ -754,7 +754,10 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         for (int w = 0; w < kWarps; ++w) s += s_red[w][threadIdx.x];
         __stcg(p.partials + ((size_t)bE * p.ntiles + tileE) * kNPart + threadIdx.x, s);
     }
-    if (EPI != kEpiStore && p.split_finalize) return;   // reduced by k_train_finalize / k_comp_finalize (next launch)
+    if (EPI != kEpiStore && p.split_finalize) {          // reduced by k_train_finalize / k_comp_finalize (next launch)
+        SFH_TL(5); SFH_TL(6);
+        return;
+    }
     __syncthreads();
     SFH_TL(5);
     if (threadIdx.x == 0) s_last = (ticket_release(p.counters + bE) == p.ntiles - 1);
