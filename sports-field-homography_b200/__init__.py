@@ -11,6 +11,7 @@ from .court import CourtTemplate, load_bundled, open_court_poi, open_court_templ
 from .dist import global_means, reduce_sums, shard_range
 from .losses import (ReprojectionLoss, consistency_loss, consistency_step, reprojection_loss,
                      reprojection_per_sample, weight_and_reduce)
+from .mapping import map_court_to_frame, map_frame_to_court
 from .post import cv2_nearest_table, postprocess_masks
 from .stage import STNWarpStage, patch_reconstructor
 from .warper import HomographyWarper, meshgrid_factors, transform_points
@@ -20,6 +21,7 @@ __all__ = [
     "CourtTemplate", "open_court_template", "open_court_poi", "load_bundled",
     "reprojection_loss", "reprojection_per_sample", "ReprojectionLoss", "weight_and_reduce",
     "consistency_loss", "consistency_step", "postprocess_masks", "cv2_nearest_table",
+    "map_frame_to_court", "map_court_to_frame",
     "shard_range", "reduce_sums", "global_means",
 ]
 __version__ = "0.1.0"

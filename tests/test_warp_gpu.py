@@ -730,6 +730,29 @@ def test_no_writes_outside_outputs_at_ragged_sizes(W, H, B):
         c()
 
 
+def test_frame_court_mapping_matches_cv2_perspective_transform():
+    """SURVEY §8 f-4 (utils/transform.py:25-55, utils/mapping_example.py): the real predicted theta_f2c of the
+    reference's example and the frame point (590, 418); cv2.perspectiveTransform is the reference's engine."""
+    cv2 = pytest.importorskip("cv2")
+    from sfh_b200 import mapping
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_real_theta.npz"))
+    thetas = g["theta"].reshape(-1, 3, 3).astype(np.float32) if "theta" in g.files else None
+    if thetas is None:
+        thetas = synth.theta_family_b(2, 1).numpy().reshape(-1, 3, 3)
+    rng = np.random.default_rng(3)
+    loc = np.concatenate([np.array([[590.0, 418.0]], dtype=np.float32), (rng.random((40, 2)) * [1280, 720]).astype(np.float32)])
+    for th in thetas:
+        pts = (loc / np.array([1280.0, 720.0], dtype=np.float32) - 0.5) * 2.0
+        ref = cv2.perspectiveTransform(pts[None].astype(np.float32), th.astype(np.float32))[0] / 2.0 + 0.5
+        got = sfh_b200.map_frame_to_court(cu(th), cu(loc), (1280, 720)).cpu().numpy()
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert np.abs(got - ref).max() <= 2e-5 * scale
+        got_b = mapping.transform_poi(cu(th)[None].expand(3, 3, 3), cu(pts)[None].expand(3, -1, -1).contiguous(), normalize=True)
+        assert np.abs(got_b.cpu().numpy() - ref[None]).max() <= 2e-5 * scale
+    with pytest.raises(ValueError):
+        sfh_b200.map_frame_to_court(cu(thetas[0])[:2], cu(loc))
+
+
 # ---------------------------------------------------------------------- API / error conventions
 def test_error_conventions_and_state_dict():
     tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 2)
