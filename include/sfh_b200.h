@@ -84,7 +84,9 @@ const char* sfh_build_info(void);
 const char* sfh_error_string(int code);
 
 /* Bytes of scratch the fused entry points need for a batch of B samples warped to HxW.
- * The workspace must be zero-filled once when it is allocated; every call leaves it zeroed. */
+ * The workspace must be zero-filled once when it is allocated and must not be written by anyone else
+ * afterwards: it carries a launch epoch (the tag of the in-launch reductions) besides the per-call partials.
+ * One workspace serves one stream at a time. */
 int64_t sfh_workspace_bytes(int B, int H, int W);
 
 /* Pack a class-index template (fp32 [Hc,Wc], every texel equal to one of palette[0..n)) into
@@ -101,13 +103,23 @@ int sfh_template_pack(const float* tmpl, int Hc, int Wc, const float* palette_ho
 int sfh_warp_fwd(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
                  int B, int H, int W, int mode, float* out, void* stream);
 
+/* Warp-stage part of Reconstructor.forward — models/reconstructor.py:185-192 — in ONE launch:
+ *   out     = warper(court_img, theta)                      [B,C,H,W] fp32   (ret['warp_mask'], :191)
+ *   poi_out = transform_poi(theta, court_poi)               [B,N,2]  fp32   (ret['poi'], :186; skipped if court_poi == NULL) */
+int sfh_forward_tail(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
+                     int B, int H, int W, int mode, float* out,
+                     const float* court_poi, int64_t court_poi_bstride, int N, float* poi_out, void* stream);
+
 /* autograd of the above w.r.t. theta (train.py:235 loss.backward() through grid_sample/bmm).
  * grad_out [B,C,H,W] fp32 -> dtheta [B,3,3] fp32.  Bilinear only (nearest has zero gradient). */
 int sfh_warp_bwd(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
                  const float* grad_out, int B, int H, int W, float* dtheta,
                  void* workspace, int64_t workspace_bytes, void* stream);
 
-/* Fused training tail, one pass over the pixels, ONE launch:
+/* Fused training tail, one pass over the pixels, ONE launch (the per-sample and batch reductions run
+ * inside it; with the environment switch SFH_TWO_LAUNCH=1 they run as a second, programmatically
+ * dependent launch instead).  int64 class ids are read through their low 32 bits: ids outside
+ * [-2^31, 2^31) differ from the reference's gt.float() (mask class ids are 0..nc-1).
  *   warp_mask = warp(theta)                               models/reconstructor.py:191
  *   L_b = mean_{h,w} crit(warp_mask, gt/nc)               train.py:194-197, models/losses.py:35-38
  *   J_b = dL_b/dtheta_b

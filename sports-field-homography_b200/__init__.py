@@ -9,8 +9,8 @@ this package is the Python mirror of the reference's call surface.  There is no 
 from . import _lib
 from .court import CourtTemplate, load_bundled, open_court_poi, open_court_template
 from .dist import global_means, reduce_sums, shard_range
-from .losses import (ReprojectionLoss, consistency_loss, consistency_step, reprojection_loss,
-                     reprojection_per_sample, weight_and_reduce)
+from .losses import (ReprojectionLoss, consistency_loss, consistency_step, per_sample_weighted_criterion,
+                     reprojection_loss, reprojection_per_sample, weight_and_reduce)
 from .mapping import map_court_to_frame, map_frame_to_court
 from .post import cv2_nearest_table, postprocess_masks
 from .stage import STNWarpStage, patch_reconstructor
@@ -20,6 +20,7 @@ __all__ = [
     "HomographyWarper", "transform_points", "meshgrid_factors", "STNWarpStage", "patch_reconstructor",
     "CourtTemplate", "open_court_template", "open_court_poi", "load_bundled",
     "reprojection_loss", "reprojection_per_sample", "ReprojectionLoss", "weight_and_reduce",
+    "per_sample_weighted_criterion",
     "consistency_loss", "consistency_step", "postprocess_masks", "cv2_nearest_table",
     "map_frame_to_court", "map_court_to_frame",
     "shard_range", "reduce_sums", "global_means",

@@ -69,6 +69,7 @@ SIGNATURES = {
     "sfh_workspace_bytes": (_L, [_I, _I, _I]),
     "sfh_template_pack": (_I, [_P, _I, _I, C.POINTER(C.c_float), _I, _P, _I, _I, _P, _P, _I, _P]),
     "sfh_warp_fwd": (_I, [_P, _T, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "sfh_forward_tail": (_I, [_P, _T, _P, _P, _I, _I, _I, _I, _P, _P, _L, _I, _P, _P]),
     "sfh_warp_bwd": (_I, [_P, _T, _P, _P, _P, _I, _I, _I, _P, _P, _L, _P]),
     "sfh_warp_loss_fwd_bwd": (_I, [_T, C.POINTER(SfhTrainTailArgs), _P]),
     "sfh_predict_tail": (_I, [_T, C.POINTER(SfhPredictTailArgs), _P]),

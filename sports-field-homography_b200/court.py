@@ -94,6 +94,9 @@ class CourtTemplate:
         self.pitch = 0
         self.sat, self.sat_pitch = None, 0
         if shared:
+            # the reference repeats ONE image B times (utils/dataset.py:59); staging reads row 0 only
+            if court_img.shape[0] > 1 and not bool((court_img == court_img[0:1]).all()):
+                raise ValueError("court_img rows differ: a shared (staged) template needs identical batch rows")
             self.f32 = court_img[0:1].contiguous()
             self.batch_stride = 0
         else:

@@ -28,6 +28,10 @@ struct PoiParams {
     // generic backward (nullable as a group)
     const float* grad_poi;    // [B,N,2]
     float* dtheta;            // [B,9]
+    // in-launch consumer (k_fused's per-sample reducer CTA): K[9] and R_b are also published as tagged
+    // 64-bit words {tag, fp32} at pub + 10*b, so the reader needs no fence (nullable)
+    unsigned long long* pub;
+    const int* epoch;         // the launch epoch; tag = *epoch + 1
 };
 
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -97,6 +101,13 @@ __device__ __forceinline__ void poi_warp(const PoiParams& p, int b, int lane) {
     for (int k = 0; k < 9; ++k) G[k] = warp_sum_d(G[k]);
     if (lane == 0 && p.gt_poi) p.Rb[b] = (float)loss;
     float* dst = p.gt_poi ? p.K : p.dtheta;
+    const bool publish = p.pub != nullptr && p.gt_poi != nullptr;
+    unsigned long long tag = 0ull;
+    if (lane == 0 && publish) {
+        tag = (unsigned long long)((unsigned)__ldcg(p.epoch) + 1u) << 32;
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p.pub + 10 * (size_t)b + 9),
+                     "l"(tag | (unsigned long long)__float_as_uint((float)loss)) : "memory");
+    }
     if (lane == 0 && dst) {
         // dtheta = -M^T G M^T :  [i][j] = -sum_{k,l} M[k][i] G[k][l] M[j][l]
 #pragma unroll
@@ -109,6 +120,9 @@ __device__ __forceinline__ void poi_warp(const PoiParams& p, int b, int lane) {
 #pragma unroll
                     for (int l = 0; l < 3; ++l) acc += m[3 * k + i] * G[3 * k + l] * m[3 * j + l];
                 dst[9 * b + 3 * i + j] = (float)(-acc);
+                if (publish)
+                    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p.pub + 10 * (size_t)b + 3 * i + j),
+                                 "l"(tag | (unsigned long long)__float_as_uint((float)(-acc))) : "memory");
             }
     }
 }

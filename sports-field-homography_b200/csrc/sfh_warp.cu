@@ -32,9 +32,12 @@ struct FusedParams {
     int ntiles;          // CTAs per sample
     int vec4;            // W % 4 == 0 and all row bases 16-byte aligned
     int use_tma;         // the CTA's gt tile (loss) / logits tile (predict) is staged in smem by one TMA load
-    int split_finalize;  // kEpiLoss: CTAs only write their partials; k_train_finalize (next launch) reduces them
+    int split_finalize;  // 1: CTAs only write their partials, k_train_finalize / k_comp_finalize (next launch) reduce them;
+                         // 0: the sample's last-dispatched CTA reduces them inside this launch (tagged slots, no fence)
     int fin_slots;       // partial slots per sample read by k_train_finalize
     int short_last;      // H % (8R) != 0: the short bottom tiles of all samples are dispatched last (shorter tail)
+    int lean, compact;   // development switches (SFH_NO_LEAN / SFH_NO_COMPACT clear them): guard-free geometry in proven-safe
+                         // patches; compacted edge-pixel pass of the bilinear epilogues
     // kEpiStore / kEpiBwd
     float* out_f;        // [B,C,H,W]
     const float* grad_out;
@@ -98,6 +101,39 @@ __device__ __forceinline__ Pix pixel_geom(const Homog& Hm, float pu0, float pu3,
     return p;
 }
 
+// The same arithmetic without the guards (|Z| <= eps -> scale 1, 1/Z subnormal, non-finite / out-of-int-range
+// coordinate -> -100).  Valid — and then bit-identical to pixel_geom — for pixels of a patch whose classification
+// proved that none of them can fire: Z keeps its sign with |Z| well above eps and below 1e37 at the four corners
+// (Z is affine in (u,v)), and the corner coordinates are finite and far inside the int range (x = X/Z and y = Y/Z
+// are monotone along rows and columns while Z keeps its sign).  16 instructions shorter per pixel.
+template <int MODE>
+__device__ __forceinline__ Pix pixel_geom_lean(const Homog& Hm, float u, float v, float Wc_f, float Hc_f) {
+    Pix p;
+    p.f.X = __fadd_rn(__fmaf_rn(v, Hm.h[1], __fmul_rn(u, Hm.h[0])), Hm.h[2]);
+    p.f.Y = __fadd_rn(__fmaf_rn(v, Hm.h[4], __fmul_rn(u, Hm.h[3])), Hm.h[5]);
+    const float Z = __fadd_rn(__fmaf_rn(v, Hm.h[7], __fmul_rn(u, Hm.h[6])), Hm.h[8]);
+    p.f.zok = true;
+    p.f.s = rcp_rn_normal(Z);
+    p.f.x = __fmul_rn(p.f.s, p.f.X);
+    p.f.y = __fmul_rn(p.f.s, p.f.Y);
+    const float ix = __fmul_rn(__fmaf_rn(__fadd_rn(p.f.x, 1.0f), Wc_f, -1.0f), 0.5f);
+    const float iy = __fmul_rn(__fmaf_rn(__fadd_rn(p.f.y, 1.0f), Hc_f, -1.0f), 0.5f);
+    if (MODE == SFH_MODE_NEAREST) {
+        p.x0 = __float2int_rn(ix);
+        p.y0 = __float2int_rn(iy);
+        p.ex = p.wx = p.sy = p.ny = 0.f;
+    } else {
+        const float fx = floorf(ix), fy = floorf(iy);
+        p.x0 = (int)fx;
+        p.y0 = (int)fy;
+        p.wx = __fsub_rn(ix, fx);
+        p.ex = __fsub_rn(1.0f, p.wx);
+        p.ny = __fsub_rn(iy, fy);
+        p.sy = __fsub_rn(1.0f, p.ny);
+    }
+    return p;
+}
+
 // ATen accumulation order: nw, ne, sw, se, each step one FMA.
 __device__ __forceinline__ float bilerp(const Pix& p, const TapVals& t) {
     float o = __fmul_rn(t.a, __fmul_rn(p.ex, p.sy));
@@ -124,6 +160,15 @@ struct GradAcc {
         xu = fmaf(gX, u, xu); x1 += gX;
         yu = fmaf(gY, u, yu); y1 += gY;
         zu = fmaf(gZ, u, zu); z1 += gZ;
+    }
+    // one isolated pixel (the compacted edge-pixel pass): straight into the nine sums
+    __device__ __forceinline__ void add_px(const Pix& p, float gix, float giy, float halfWc, float halfHc, float u, float v) {
+        const float gx = gix * halfWc, gy = giy * halfHc;
+        const float gX = gx * p.f.s, gY = gy * p.f.s;
+        const float gZ = p.f.zok ? -(gx * p.f.X + gy * p.f.Y) * p.f.s * p.f.s : 0.f;
+        a[0] = fmaf(gX, u, a[0]); a[1] = fmaf(gX, v, a[1]); a[2] += gX;
+        a[3] = fmaf(gY, u, a[3]); a[4] = fmaf(gY, v, a[4]); a[5] += gY;
+        a[6] = fmaf(gZ, u, a[6]); a[7] = fmaf(gZ, v, a[7]); a[8] += gZ;
     }
     __device__ __forceinline__ void end_row(float v) {
         a[0] += xu; a[1] = fmaf(x1, v, a[1]); a[2] += x1;
@@ -260,7 +305,18 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
 #endif
 constexpr int min_ctas(int epi) { return (epi == kEpiStore || epi == kEpiPredict) ? SFH_MINCTAS_LIGHT : SFH_MINCTAS_HEAVY; }
 
+constexpr int kEpochIdx = 65590; // launch epoch inside the fixed ticket area of the workspace (kTicketBytes / 4 = 65600 ints)
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 constexpr int kMaxR = 16;        // bands (8 rows each) per CTA
+constexpr int kListCap = 32 + 128;   // a patch adds <= 128 pixels to a list that is drained below 32 after every patch
 constexpr int kPatchW = 16;      // a warp works on 16 x 8 pixel patches: lane = (ly 0..7, lx 0..3), 4 px per lane
 constexpr float kBoxMargin = 1.0f / 64.0f;   // slack (in texels) on the patch bounding box, >> fp32 rounding of ix
 
@@ -301,12 +357,8 @@ __device__ __forceinline__ void tl_stamp(int cta, int phase) {
     }
 }
 #define SFH_TL(phase) tl_stamp((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, phase)
-// streaming kernel: stamps of the first 8 tiles of every CTA, taken by lane 0 of warp 1 (phases 0-4) and warp 0 (5-7)
-#define SFH_TLS(w, phase) do { if (g_timeline && i < 8 && warp == (w) && lane == 0) { unsigned long long t_; \
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_timeline[((size_t)blockIdx.x * 8 + i) * 8 + (phase)] = (long long)t_; } } while (0)
 #else
 #define SFH_TL(phase)
-#define SFH_TLS(w, phase)
 #endif
 
 // (sample, tile row) of this CTA.  CTAs are dispatched x-fastest, then y, then z.  With `short_last`
@@ -328,12 +380,24 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     extern __shared__ __align__(128) unsigned char s_dyn[];            // TMA destination (gt tile)
     __shared__ __align__(16) float s_tab[Taps<FMT>::kSmemFloats];
     __shared__ float s_red[kWarps][16];
-    __shared__ double s_fin[kNPart][kFinGroup];
-    __shared__ float s_gx[kMaxR + 1][kWarps + 1], s_gy[kMaxR + 1][kWarps + 1], s_gz[kMaxR + 1][kWarps + 1];
-    __shared__ unsigned short s_items[kMaxR * kWarps];   // patch id | (class+1) << 8, edge patches first
+    // one scratch area, three tenants with disjoint lifetimes (3 CTAs/SM leave no smem to spare next to the 64 KiB
+    // gt tile): the corner grid (prologue, dead after the classification barrier), the per-warp edge-pixel lists
+    // (patch loop), the fp64 partial sums of the reducer CTA (after the end-of-loop barrier)
+    constexpr int kFinBytes = (int)sizeof(double) * kNPart * kFinGroup;                 // 2016
+    constexpr int kGridBytes = 3 * (kMaxR + 1) * (kWarps + 1) * (int)sizeof(float);     // 1836
+    constexpr int kListBytes = kWarps * kListCap * (int)sizeof(unsigned short);         // 2560
+    static_assert(kListBytes <= kFinBytes + kGridBytes, "lists must fit the shared scratch area");
+    __shared__ __align__(16) unsigned char s_scratch[kFinBytes + kGridBytes];
+    double (*s_fin)[kFinGroup] = reinterpret_cast<double (*)[kFinGroup]>(s_scratch);
+    float (*s_gx)[kWarps + 1] = reinterpret_cast<float (*)[kWarps + 1]>(s_scratch + kFinBytes);
+    float (*s_gy)[kWarps + 1] = s_gx + (kMaxR + 1);
+    float (*s_gz)[kWarps + 1] = s_gy + (kMaxR + 1);
+    // per warp: edge pixels (row << 7 | col inside the CTA tile) awaiting the compacted pass
+    unsigned short (*s_list)[kListCap] = reinterpret_cast<unsigned short (*)[kListCap]>(s_scratch);
+    __shared__ unsigned short s_items[kMaxR * kWarps];   // patch id | (class+1) << 8 | lean << 15, edge patches first
     __shared__ int s_ecnt[kWarps];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_last;
+    __shared__ unsigned s_epoch;
 
     // the loss epilogue always samples bilinearly; its MODE argument carries the criterion instead
     constexpr int SMODE = (EPI == kEpiLoss) ? SFH_MODE_BILINEAR : MODE;
@@ -360,6 +424,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     // previous kernel of the stream (e.g. the previous step's finalize) is still running; everything
     // that touches global memory comes after this wait (no-op when launched without the attribute).
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (EPI != kEpiStore && !p.split_finalize && p.counters && threadIdx.x == 32)   // read long before it is needed
+        s_epoch = (unsigned)__ldcg(p.counters + kEpochIdx);                          // (the first barrier publishes it)
     if (tma && threadIdx.x == 0) {
         // the tile's streaming input is requested before anything else so that it arrives behind
         // the whole prologue (evict-first in L2: it is read exactly once)
@@ -373,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             tma_load_4d(s_dyn, &p.gt_map, tx * (kTileW / 2), band0 >> 1, 0, b, &s_bar, pol);
         }
     }
-    if ((EPI == kEpiLoss || EPI == kEpiPredict) && tile == 0 && p.poi.court_poi)
+    if (EPI != kEpiBwd && tile == 0 && p.poi.court_poi)
         poi_block(p.poi, b);                 // first warp: the 52/33 court points in fp64
     Homog Hm;
     Hm.load(p.theta + 9 * b);
@@ -394,6 +460,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     SFH_TL(1);
     taps.init(p.t, b, s_tab);
     int cls = -1;
+    bool lean = false;                       // guards of the per-pixel geometry provably idle in this patch (pixel_geom_lean)
     if (classify && threadIdx.x < nitems) {
         const int r = threadIdx.x / kWarps, k = threadIdx.x % kWarps;
         const float x00 = s_gx[r][k], x01 = s_gx[r][k + 1], x10 = s_gx[r + 1][k], x11 = s_gx[r + 1][k + 1];
@@ -408,6 +475,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                          (y00 == y00) & (y01 == y01) & (y10 == y10) & (y11 == y11) &
                          (xmin > -1e9f) & (xmax < 1e9f) & (ymin > -1e9f) & (ymax < 1e9f);
         if ((zpos | zneg) & fin) {
+            // |Z| over the patch >= the smallest corner |Z| (affine, one sign); the margin covers the fp32 rounding
+            // of Z at interior pixels (<= 4 ulp of |h6|+|h7|+|h8|), so no pixel can take the |Z| <= eps or the
+            // subnormal-reciprocal branch, and the corner bound keeps every coordinate far inside the int range
+            const float Mz = fabsf(Hm.h[6]) + fabsf(Hm.h[7]) + fabsf(Hm.h[8]);
+            const float zmin = fminf(fminf(fabsf(z00), fabsf(z01)), fminf(fabsf(z10), fabsf(z11)));
+            lean = (zmin > 1e-6f * Mz + 1e-7f) & (Mz < 1e30f) & (p.lean != 0);
             // packed-template entries any pixel of the patch can touch (bilinear: floor+1,
             // nearest: rint+1 <= floor+2), clamped onto the all-zero border like the sampler does
             const int wmax = p.t.width + 1, hmax = p.t.height + 1;
@@ -437,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             if (w < warp) before += c;
         }
         const int pos = is_edge ? before : total + ((int)threadIdx.x - before);
-        s_items[pos] = (unsigned short)(threadIdx.x | ((cls + 1) << 8));
+        s_items[pos] = (unsigned short)(threadIdx.x | ((cls + 1) << 8) | (lean ? 0x8000 : 0));
     }
     __syncthreads();
 
@@ -455,10 +528,60 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     if (tma) mbar_wait(&s_bar, 0);           // gt tile has landed (it streamed in behind the prologue)
     SFH_TL(3);
 
+    // ---- compacted edge-pixel pass (bilinear Store / Bwd / Loss epilogues on packed templates) -----------------
+    // In a patch that touches a class edge only the pixels whose OWN 2x2 footprint straddles the edge (3-4 % of
+    // all pixels) need weights, interpolation and the chain rule; every other pixel samples one class and is a
+    // constant with zero gradient, exactly like the pixels of an edge-free patch.  The patch pass therefore only
+    // computes each pixel's exact texel coordinates and looks at its packed entry; pixels with a mixed entry are
+    // appended to a per-warp list and processed 32 at a time — one pixel per lane, all lanes busy — by flush().
+    constexpr bool kCompact = (FMT != SFH_TMPL_F32) && (SMODE == SFH_MODE_BILINEAR) &&
+                              (EPI == kEpiStore || EPI == kEpiBwd || EPI == kEpiLoss);
+    int ncnt = 0;                            // entries in this warp's list (warp-uniform)
+    auto flush = [&](int n) {                // the top n (<= 32) entries of the list
+        __syncwarp();
+        if (lane < n) {
+            const unsigned e = s_list[warp][ncnt - n + lane];
+            const int r = (int)(e >> 7), c = (int)(e & 127u);
+            const int prow = band0 + r, pcol = tx * kTileW + c;                 // inside the image by construction
+            const float uu = p.xs ? __ldg(p.xs + pcol) : mesh_coord(pcol, W);
+            const float vv = p.ys ? __ldg(p.ys + prow) : mesh_coord(prow, H);
+            const Pix q = pixel_geom_lean<SFH_MODE_BILINEAR>(Hm, uu, vv, Wc_f, Hc_f);
+            const TapVals t = taps.fetch4(0, q.x0, q.y0);
+            const size_t pix = base_b + (unsigned)(prow * W + pcol);
+            float g = 0.f;
+            if (EPI == kEpiStore || EPI == kEpiLoss) {
+                const float o = bilerp(q, t);
+                if (EPI == kEpiStore || p.out_f) p.out_f[pix] = o;
+                if (EPI == kEpiLoss) {
+                    float gfv;
+                    if (p.gt8) gfv = (float)(tma ? s_dyn[r * kTileW + c] : p.gt8[pix]);
+                    else gfv = (float)(int)(tma ? s_gt[r * kTileW + c] : p.gt[pix]);
+                    const float tg = p.nc_pow2 ? __fmul_rn(gfv, p.inv_nc) : __fdiv_rn(gfv, ncf);
+                    const float d = o - tg;
+                    float l;
+                    if (kMse || fabsf(d) < 1.0f) { l = d * d; g = d; }
+                    else { l = 2.0f * fabsf(d) - 1.0f; g = d > 0.f ? 1.0f : -1.0f; }
+                    loss_sum += l;
+                    g *= gscale;
+                }
+            } else {
+                g = __ldcs(p.grad_out + pix);
+            }
+            if (EPI != kEpiStore) {
+                const float gix = ((t.b - t.a) * q.sy + (t.d - t.c) * q.ny) * g;
+                const float giy = ((t.c - t.a) * q.ex + (t.d - t.b) * q.wx) * g;
+                acc.add_px(q, gix, giy, halfWc, halfHc, uu, vv);
+            }
+        }
+        ncnt -= n;
+        __syncwarp();
+    };
+
 #pragma unroll 1
     for (int it = warp; it < nitems; it += kWarps) {
         const unsigned item = s_items[it];
-        const int pr = (item & 0xffu) >> 3, pk = item & 7u, pc = (int)(item >> 8) - 1;
+        const int pr = (item & 0xffu) >> 3, pk = item & 7u, pc = (int)((item >> 8) & 0x7fu) - 1;
+        const bool lean_patch = (item & 0x8000u) != 0u;
         const int row = band0 + pr * 8 + ly;
         const int col = tx * kTileW + pk * kPatchW + lx * 4;
         const bool row_ok = FT || row < H;
@@ -552,6 +675,54 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             continue;                        // kEpiBwd: zero gradient, grad_out is not even read
         }
 
+        if (kCompact && lean_patch && p.compact) {
+            // ============ edge patch, compacted: constants here, mixed-footprint pixels to the list ============
+            const float v = p.ys ? __ldg(p.ys + rowc) : mesh_coord(rowc, H);
+            unsigned ent[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {    // exact texel coordinates (no weights), four entry loads in flight
+                const int cx = FT ? col + j : min(col + j, W - 1);
+                const float uj = p.xs ? __ldg(p.xs + cx) : mesh_coord(cx, W);
+                const Pix q = pixel_geom_lean<SFH_MODE_BILINEAR>(Hm, uj, v, Wc_f, Hc_f);
+                ent[j] = taps.quad(q.x0, q.y0);
+            }
+            float o[4];
+            unsigned em = 0u;                // pixels whose footprint mixes classes
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const TapVals t = taps.decode(ent[j]);
+                o[j] = t.a;                  // uniform footprint: the class value (a == b == c == d)
+                if (!t.uni && SFH_PIX_OK(j)) em |= 1u << j;
+            }
+            if (EPI == kEpiStore || (EPI == kEpiLoss && p.out_f)) {
+                // mixed pixels are rewritten by flush(); __syncwarp orders the two stores
+                if (vec) __stcs((float4*)(p.out_f + rowbase), make_float4(o[0], o[1], o[2], o[3]));
+                else
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_f[rowbase + j] = o[j];
+            }
+            if (EPI == kEpiLoss) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d = o[j] - tgt[j];
+                    float l = (kMse || fabsf(d) < 1.0f) ? d * d : 2.0f * fabsf(d) - 1.0f;
+                    if (!SFH_PIX_OK(j) || ((em >> j) & 1u)) l = 0.f;
+                    loss_sum += l;
+                }
+            }
+            const unsigned below = (1u << lane) - 1u;
+            const unsigned id0 = (unsigned)((pr * 8 + ly) << 7) | (unsigned)(pk * kPatchW + lx * 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool m = (em >> j) & 1u;
+                const unsigned bl = __ballot_sync(0xffffffffu, m);
+                if (m) s_list[warp][ncnt + __popc(bl & below)] = (unsigned short)(id0 + j);
+                ncnt += __popc(bl);
+            }
+            while (ncnt >= 32) flush(32);
+            continue;
+        }
+
         // ======================= per-pixel path (patch touches a class edge) ====================
         const float v = p.ys ? __ldg(p.ys + rowc) : mesh_coord(rowc, H);
         float u[4];
@@ -567,10 +738,15 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         }
         Pix px[4];
         if (EPI != kEpiLoss) {
+            if (lean_patch) {                // warp-uniform: the guards cannot fire anywhere in this patch
 #pragma unroll
-            for (int j = 0; j < 4; ++j)      // u*h{0,3,6}: the first product of the bmm chain
-                px[j] = pixel_geom<SMODE>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]), __fmul_rn(u[j], Hm.h[6]),
-                                         v, Wc_f, Hc_f);
+                for (int j = 0; j < 4; ++j) px[j] = pixel_geom_lean<SMODE>(Hm, u[j], v, Wc_f, Hc_f);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)  // u*h{0,3,6}: the first product of the bmm chain
+                    px[j] = pixel_geom<SMODE>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]), __fmul_rn(u[j], Hm.h[6]),
+                                             v, Wc_f, Hc_f);
+            }
         }
 
         if (EPI == kEpiStore || EPI == kEpiBwd) {
@@ -721,6 +897,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         }
     }
 #undef SFH_PIX_OK
+    if (kCompact && ncnt > 0) flush(ncnt);   // the remainder (< 32 pixels)
 
     if (EPI == kEpiStore) return;
     if (EPI == kEpiPredict && !(p.score && p.ratio != 0)) return;
@@ -748,29 +925,44 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         if (!(lane & 1)) s_red[warp][((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = tot;
     }
     __syncthreads();
+    // One partial per (sample, tile, component) in a fixed slot.  In-launch reduction (split_finalize == 0):
+    // a slot is ONE 64-bit word {tag, fp32 value}; the tag is this launch's epoch, so a reader that sees the
+    // tag has the value as well (single-copy atomicity of an aligned 8-byte store) and the 1900+ producer
+    // CTAs retire without any fence or ticket.  The sample's last-dispatched CTA (highest linear block index
+    // among the sample's tiles; CTAs are dispatched in index order, so everything it waits for is already
+    // resident or done) polls the sample's slots and adds them in fixed order in fp64.
+    const unsigned want = p.split_finalize ? 0u : s_epoch + 1u;
     if (threadIdx.x < kNPart) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) s += s_red[w][threadIdx.x];
-        __stcg(p.partials + ((size_t)bE * p.ntiles + tileE) * kNPart + threadIdx.x, s);
+        const size_t slot = ((size_t)bE * p.ntiles + tileE) * kNPart + threadIdx.x;
+        if (p.split_finalize) __stcg(p.partials + slot, s);
+        else st_relaxed_u64(reinterpret_cast<unsigned long long*>(p.partials) + slot,
+                            ((unsigned long long)want << 32) | (unsigned long long)__float_as_uint(s));
     }
-    if (EPI != kEpiStore && p.split_finalize) {          // reduced by k_train_finalize / k_comp_finalize (next launch)
-        SFH_TL(5); SFH_TL(6);
-        return;
-    }
-    __syncthreads();
-    SFH_TL(5);
-    if (threadIdx.x == 0) s_last = (ticket_release(p.counters + bE) == p.ntiles - 1);
-    SFH_TL(6);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();   // acquire side, once per sample
+    SFH_TL(5); SFH_TL(6);
+    if (p.split_finalize) return;                        // reduced by k_train_finalize / k_comp_finalize (next launch)
+    if (tileE != p.ntiles - 1) return;
     {
         const int k = threadIdx.x / kFinGroup, jj = threadIdx.x % kFinGroup;
         if (k < kNPart) {
             double s = 0.0;
-            const float* base = p.partials + (size_t)bE * p.ntiles * kNPart + k;
-            for (int t = jj; t < p.ntiles; t += kFinGroup) s += (double)__ldcg(base + (size_t)t * kNPart);
+            const unsigned long long* base = reinterpret_cast<const unsigned long long*>(p.partials) + (size_t)bE * p.ntiles * kNPart + k;
+            for (int t0 = jj; t0 < p.ntiles; t0 += 4 * kFinGroup) {
+                unsigned long long w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {            // four polls in flight
+                    const int tt = t0 + u * kFinGroup;
+                    w[u] = (tt < p.ntiles) ? ld_relaxed_u64(base + (size_t)tt * kNPart) : ((unsigned long long)want << 32);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int tt = t0 + u * kFinGroup;
+                    while ((unsigned)(w[u] >> 32) != want) w[u] = ld_relaxed_u64(base + (size_t)tt * kNPart);
+                    s += (double)__uint_as_float((unsigned)w[u]);
+                }
+            }
             s_fin[k][jj] = s;
         }
     }
@@ -790,9 +982,11 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             if (k == 10) p.score[bE] = (float)(s / ((double)p.lh * (double)p.lw));
         }
     }
+    bool counted = false;
     if (EPI == kEpiLoss && p.loss_out) {
         // ---- weighting + batch mean + total dtheta, still inside the same launch ------------
         __syncthreads();
+        counted = true;
         if (warp == 0) {
             const int B = p.B;
             double w_eff = 1.0;
@@ -808,15 +1002,19 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             }
             const bool rep = p.poi.gt_poi != nullptr;
             const double cr = (double)p.rec_lambda * w_eff, cp = (double)p.reproj_lambda;
-            if (lane < 9) {
-                const double Kk = rep ? (double)__ldcg(p.poi.K + 9 * bE + lane) : 0.0;
-                p.dtheta_total[9 * bE + lane] = (float)((cr * s_fin[1 + lane][0] + cp * Kk) / (double)B);
+            // dR_b/dtheta (lanes 0-8) and R_b (lane 9) come from the sample's POI warp (tile 0) as tagged words
+            double KR = 0.0;
+            if (rep && lane < 10) {
+                unsigned long long w;
+                do { w = ld_relaxed_u64(p.poi.pub + 10 * (size_t)bE + lane); } while ((unsigned)(w >> 32) != want);
+                KR = (double)__uint_as_float((unsigned)w);
             }
+            const double Rv = __shfl_sync(0xffffffffu, KR, 9);
+            if (lane < 9) p.dtheta_total[9 * bE + lane] = (float)((cr * s_fin[1 + lane][0] + cp * KR) / (double)B);
             int last2 = 0;
             if (lane == 0) {
-                const double Rv = rep ? (double)__ldcg(p.poi.Rb + bE) : 0.0;
                 __stcg(p.contrib + bE, cr * s_fin[0][0] + cp * Rv);
-                last2 = (ticket_release(p.counters + B) == B - 1);
+                last2 = (ticket_release(p.counters + B) == B - 1);    // B fences per launch (one per sample), not one per CTA
             }
             last2 = __shfl_sync(0xffffffffu, last2, 0);
             if (last2) {                    // last sample of the batch: fixed-order sum over bE
@@ -824,429 +1022,22 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                 double s = 0.0;
                 for (int i = lane; i < B; i += 32) s += __ldcg(p.contrib + i);
                 s = warp_sum(s);
-                if (lane == 0) { *p.loss_out = (float)(s / (double)B); p.counters[B] = 0; }
-            }
-        }
-    }
-    if (threadIdx.x == 0) p.counters[bE] = 0;   // leave the workspace zeroed for the next call
-}
-
-// ------------------------------------------------------------------------------------------
-// Streaming training kernel (kEpiLoss with TMA-staged gt tiles): k_fused's loss epilogue turned
-// into a persistent loop so that the per-CTA fixed costs (tables, barriers, launch gaps, the
-// ticket's MEMBAR) are paid once per CTA instead of once per tile, and a gt tile is always in
-// flight while the previous one is being consumed.
-//
-//   * grid = resident CTAs only (3 per SM); CTA c walks tiles c, c+G, c+2G, ... (128 x 8*kLR px)
-//   * a kLS-stage ring of gt tiles in smem; lane 0 of warp 0 issues the TMA load of tile i+kLS-1
-//     once every warp has released the stage (`empty` mbarrier, 8 arrivals), all warps wait on
-//     the stage's `full` mbarrier.  No __syncthreads in the loop: warps run up to a stage apart.
-//   * every warp classifies the tile's <= 32 patches itself (one lane per patch; redundant across
-//     warps but sync-free); the summed-area-table loads of tile i+1 are issued before tile i is
-//     processed, so their latency is hidden behind the pixel work
-//   * per tile every warp writes its 10 sums to the fixed slot (tile, warp): results do not depend
-//     on which CTA ran which tile.  k_train_finalize then adds every sample's slots in fixed
-//     order in fp64 and applies the optional weighting / batch mean / total dtheta.
-// ------------------------------------------------------------------------------------------
-#ifndef SFH_LR
-#define SFH_LR 4
-#endif
-#ifndef SFH_LS
-#define SFH_LS 3
-#endif
-#ifndef SFH_STREAM_CTAS
-#define SFH_STREAM_CTAS 2   // 128 registers: no spills; measured faster than 3 CTAs/SM at 80
-#endif
-constexpr int kLR = SFH_LR;                      // bands per tile: 128 x 8*kLR px
-constexpr int kLS = SFH_LS;                      // ring stages
-constexpr int kLItems = kLR * kWarps;            // patches per tile, one lane each
-static_assert(kLItems <= 32, "one lane per patch");
-constexpr int kLStageBytes = kLR * 8 * kTileW * 8;
-constexpr int kLMaxB = 1024;                     // theta table in smem: 36 B per sample
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-
-// classification of one patch, split in two so the table loads can be in flight across a tile
-struct ClsPend {
-    unsigned ec, s11, s01, s10, s00;
-    bool box;                                    // the 4-corner bounding box is usable
-};
-
-template <int FMT>
-__device__ __forceinline__ ClsPend classify_issue(const FusedParams& p, const Taps<FMT>& taps, const float* th,
-                                                  int tx, int band0, int id, bool active) {
-    ClsPend c;
-    c.box = false;
-    c.ec = c.s11 = c.s01 = c.s10 = c.s00 = 0u;
-    if ((FMT == SFH_TMPL_F32) || p.t.sat == nullptr || !active) return c;
-    const int H = p.H, W = p.W;
-    const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
-    Homog Hm;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) Hm.h[k] = th[k];
-    const int r = id / kWarps, k = id % kWarps;
-    float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
-    bool zpos = true, zneg = true, fin = true;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int grow = min(band0 + 8 * (r + (q >> 1)), H - 1);
-        const int gcol = min(tx * kTileW + kPatchW * (k + (q & 1)), W - 1);
-        const float gu = p.xs ? __ldg(p.xs + gcol) : mesh_coord(gcol, W);
-        const float gv = p.ys ? __ldg(p.ys + grow) : mesh_coord(grow, H);
-        const Flow f = flow_at(Hm, __fmul_rn(gu, Hm.h[0]), __fmul_rn(gu, Hm.h[3]), __fmul_rn(gu, Hm.h[6]), gv);
-        const float gx = __fmul_rn(__fmaf_rn(__fadd_rn(f.x, 1.0f), Wc_f, -1.0f), 0.5f);
-        const float gy = __fmul_rn(__fmaf_rn(__fadd_rn(f.y, 1.0f), Hc_f, -1.0f), 0.5f);
-        xmin = fminf(xmin, gx); xmax = fmaxf(xmax, gx);
-        ymin = fminf(ymin, gy); ymax = fmaxf(ymax, gy);
-        fin &= (gx == gx) & (gy == gy);
-        zpos &= f.zok & (f.s > 0.f);          // Z of one sign at the 4 corners => no horizon inside
-        zneg &= f.zok & (f.s < 0.f);
-    }
-    fin &= (xmin > -1e9f) & (xmax < 1e9f) & (ymin > -1e9f) & (ymax < 1e9f);
-    if ((zpos | zneg) & fin) {
-        const int wmax = p.t.width + 1, hmax = p.t.height + 1;
-        const int i0 = min(max(__float2int_rd(xmin - kBoxMargin) + 1, 0), wmax);
-        const int i1 = min(max(__float2int_rd(xmax + kBoxMargin) + 2, 0), wmax);
-        const int j0 = min(max(__float2int_rd(ymin - kBoxMargin) + 1, 0), hmax);
-        const int j1 = min(max(__float2int_rd(ymax + kBoxMargin) + 2, 0), hmax);
-        const unsigned* S = p.t.sat;
-        const int sp = p.t.sat_pitch;
-        c.box = true;
-        c.ec = taps.entry_class(i0, j0);
-        c.s11 = __ldg(S + (j1 + 1) * sp + (i1 + 1));
-        c.s01 = __ldg(S + j0 * sp + (i1 + 1));
-        c.s10 = __ldg(S + (j1 + 1) * sp + i0);
-        c.s00 = __ldg(S + j0 * sp + i0);
-    }
-    return c;
-}
-__device__ __forceinline__ int classify_finish(const ClsPend& c) {      // class of an edge-free patch, else -1
-    return (c.box && (c.s11 - c.s01 - c.s10 + c.s00) == 0u) ? (int)c.ec : -1;
-}
-
-constexpr int kLLook = kWarps;                   // tile i's patch list is built by warp i % 8 while it works on tile i - 8
-constexpr int kLSlots = 2 * kLLook;              // list ring
-constexpr int kLStash = (kLItems + kWarps - 2) / (kWarps - 1);   // edge patches one of warps 1..7 can get from a tile
-
-template <int FMT, bool FT, bool KMSE>
-__global__ void __launch_bounds__(kThreads, SFH_STREAM_CTAS) k_train_stream(const __grid_constant__ FusedParams p) {
-    extern __shared__ __align__(128) unsigned char s_dyn[];            // kLS gt stages, then theta [B][9]
-    __shared__ __align__(16) float s_tab[Taps<FMT>::kSmemFloats];
-    __shared__ unsigned short s_list[kLSlots][32];                     // ring of per-tile patch lists
-    __shared__ int s_lcount[kLSlots];                                  // ... and their number of edge entries
-    __shared__ __align__(8) uint64_t s_full[kLS], s_empty[kLS], s_lfull[kLSlots];
-
-    const int H = p.H, W = p.W;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int lx = lane & 3, ly = lane >> 2;
-    const float Wc_f = (float)p.t.width, Hc_f = (float)p.t.height;
-    const int tiles_x = (W + kTileW - 1) / kTileW;
-    const int tps = p.ntiles;                                          // tiles per sample
-    const int tiles_y = tps / tiles_x;
-    const int total = tps * p.B;
-    const int G = (int)gridDim.x;
-    const int n = (total - (int)blockIdx.x + G - 1) / G;               // tiles of this CTA: blockIdx.x + i*G
-    const uint32_t tile_bytes = (uint32_t)(kLR * 8 * kTileW) * (p.gt8 ? 1u : 8u);
-    float* s_theta = reinterpret_cast<float*>(s_dyn + kLS * kLStageBytes);
-    const uint64_t pol = l2_policy_evict_first();
-
-    auto tile_coords = [&](int i, int& b, int& tx, int& ty) {          // divisions: used off the per-tile path only
-        const int t = (int)blockIdx.x + i * G;
-        b = t / tps;
-        const int rem = t - b * tps;
-        ty = rem / tiles_x;
-        tx = rem - ty * tiles_x;
-    };
-    auto issue_tile = [&](int j) {                                     // one thread
-        int b, tx, ty;
-        tile_coords(j, b, tx, ty);
-        const int sj = j % kLS;
-        mbar_expect_tx(&s_full[sj], tile_bytes);
-        tma_load_3d(s_dyn + (size_t)sj * kLStageBytes, &p.gt_map, tx * kTileW, ty * (8 * kLR), b, &s_full[sj], pol);
-    };
-    // the patch list of tile j: classify (table loads in flight) ... finish (ballot, edge patches first)
-    auto list_issue = [&](int j, const Taps<FMT>& taps, int& nitems) {
-        int b, tx, ty;
-        tile_coords(j, b, tx, ty);
-        nitems = min(kLR, (H - ty * (8 * kLR) + 7) >> 3) * kWarps;
-        return classify_issue<FMT>(p, taps, s_theta + 9 * b, tx, ty * (8 * kLR), lane, lane < nitems);
-    };
-    auto list_finish = [&](int j, const ClsPend& pend, int nitems) {
-        const int cls = classify_finish(pend);
-        const bool is_edge = (lane < nitems) && cls < 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, is_edge);
-        const int before = __popc(bal & ((1u << lane) - 1u));
-        unsigned short* l = s_list[j % kLSlots];
-        if (lane < nitems) l[is_edge ? before : __popc(bal) + (lane - before)] = (unsigned short)(lane | ((cls + 1) << 8));
-        if (lane == 0) s_lcount[j % kLSlots] = __popc(bal);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_lfull[j % kLSlots]);             // release: the list is visible to its waiters
-    };
-
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < kLS; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_full[s])), "r"(1) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_empty[s])), "r"(kWarps) : "memory");
-        }
-#pragma unroll
-        for (int s = 0; s < kLSlots; ++s)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_lfull[s])), "r"(1) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int j = 0; j < kLS - 1 && j < n; ++j) issue_tile(j);      // streams in behind the prologue
-    }
-    Taps<FMT> taps;
-    taps.build_tables(p.t, s_tab);
-    for (int i = threadIdx.x; i < 9 * p.B; i += kThreads) s_theta[i] = __ldg(p.theta + i);
-    __syncthreads();
-    taps.init(p.t, 0, s_tab);
-    if (warp < n) {                                                    // lists of the first 8 tiles: one per warp
-        int nit;
-        const ClsPend pend = list_issue(warp, taps, nit);
-        list_finish(warp, pend, nit);
-    }
-
-    const float halfWc = 0.5f * Wc_f, halfHc = 0.5f * Hc_f;
-    const float gscale = (KMSE ? 2.0f : 1.0f) * p.invN;
-    const float ncf = (float)p.nc;
-    GradAcc acc;
-    acc.zero();
-    float loss_sum = 0.f;
-    int erot = 0;                                                      // edge patches dealt so far, mod 7
-
-    // tile walk without divisions: G = dB * tps + dY * tiles_x + dX
-    const int dB = G / tps, dY = (G - dB * tps) / tiles_x, dX = G - dB * tps - dY * tiles_x;
-    int b, tx, ty;
-    tile_coords(0, b, tx, ty);
-    int t = (int)blockIdx.x;
-
-#pragma unroll 1
-    for (int i = 0; i < n; ++i) {
-        const int band0 = ty * (8 * kLR);
-        const int nitems = min(kLR, (H - band0 + 7) >> 3) * kWarps;
-        const int s = i % kLS;
-
-        SFH_TLS(1, 0); SFH_TLS(0, 5);
-        // producer duty: refill the stage tile i-1 has just left
-        if (warp == 0) {
-            const int j = i + kLS - 1;
-            if (j < n && lane == 0) {
-                mbar_wait(&s_empty[j % kLS], ((j / kLS) & 1) ^ 1);
-                issue_tile(j);
-            }
-            __syncwarp();
-        }
-        if (warp == kWarps - 1 && t == b * tps && p.poi.court_poi) poi_warp(p.poi, b, lane);   // the sample's court points (fp64)
-
-        // list duty: this warp builds the list of tile i+8 around its own pixel work
-        const bool lister = (warp == (i & (kLLook - 1))) && (i + kLLook < n);
-        ClsPend pend = ClsPend();
-        int pend_items = 0;
-        if (lister) pend = list_issue(i + kLLook, taps, pend_items);
-
-        mbar_wait(&s_lfull[i % kLSlots], (i / kLSlots) & 1);           // this tile's list
-        const unsigned short* list = s_list[i % kLSlots];
-        SFH_TLS(1, 1);
-        Homog Hm;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Hm.h[k] = s_theta[9 * b + k];
-        const unsigned char* s_tile = s_dyn + (size_t)s * kLStageBytes;
-        const size_t base_b = (size_t)b * H * W;
-        float* outb = p.out_f ? p.out_f + base_b : nullptr;
-        bool had_edge = false;
-
-        mbar_wait(&s_full[s], (i / kLS) & 1);                          // gt tile has landed
-        SFH_TLS(1, 2); SFH_TLS(0, 6);
-#define SFH_PIX_OK(j) (FT || (row_ok && col + (j) < W))
-        // Dealing: list entries [0, E) touch a class edge (per-pixel path, ~10x the cost of an
-        // edge-free patch).  They go round-robin to warps 1..7 with an offset that continues
-        // across tiles (erot = edge patches dealt so far mod 7), so every warp gets the same
-        // share over time; warp 0 keeps to edge-free patches and is never late for its producer
-        // duty.  A warp first consumes everything it needs from the staged gt tile (edge-free
-        // patches are finished, edge patches keep their 128 class ids in one register per patch),
-        // releases the stage, and only then does the per-pixel work, which therefore overlaps the
-        // refill of the stage and the other warps' streaming.
-        const int E = s_lcount[i % kLSlots];
-        int q0 = (warp - 1) - erot;                                    // first edge entry of this warp
-        if (q0 < 0) q0 += kWarps - 1;
-        if (warp == 0) q0 = E;
-        erot = (erot + E) % (kWarps - 1);
-        unsigned stash[kLStash];
-        bool fits = true;                                              // every gt value of my edge patches is in 0..255
-#pragma unroll
-        for (int k = 0; k < kLStash; ++k) {
-            stash[k] = 0u;
-            const int q = q0 + k * (kWarps - 1);
-            if (q < E) {
-                const unsigned item = list[q];
-                const int soff = (((item & 0xffu) >> 3) * 8 + ly) * kTileW + (item & 7u) * kPatchW + lx * 4;
-                if (p.gt8) {
-                    stash[k] = *reinterpret_cast<const unsigned*>(s_tile + soff);
-                } else {
-                    const longlong2* sp2 = reinterpret_cast<const longlong2*>(reinterpret_cast<const long long*>(s_tile) + soff);
-                    const longlong2 glo = sp2[0], ghi = sp2[1];
-                    const int g0 = (int)glo.x, g1 = (int)glo.y, g2 = (int)ghi.x, g3 = (int)ghi.y;
-                    fits &= ((unsigned)(g0 | g1 | g2 | g3) < 256u);
-                    stash[k] = (unsigned)g0 | ((unsigned)g1 << 8) | ((unsigned)g2 << 16) | ((unsigned)g3 << 24);
+                if (lane == 0) {
+                    *p.loss_out = (float)(s / (double)B);
+                    p.counters[B] = 0;
+                    p.counters[kEpochIdx] = (int)want;       // next launch's tag
                 }
             }
         }
-        fits = __all_sync(0xffffffffu, fits);
-#pragma unroll 1
-        for (int q = E + warp; q < nitems; q += kWarps) {              // edge-free patches: constant, zero gradient
-            const unsigned item = list[q];
-            const int pr = (item & 0xffu) >> 3, pk = item & 7u, pc = (int)(item >> 8) - 1;
-            const int row = band0 + pr * 8 + ly;
-            const int col = tx * kTileW + pk * kPatchW + lx * 4;
-            const bool row_ok = FT || row < H;
-            const int rowc = FT ? row : min(row, H - 1);
-            const bool vec = FT || (p.vec4 && row_ok && col + 3 < W);
-            const int off = rowc * W + col;
-            const int soff = (pr * 8 + ly) * kTileW + pk * kPatchW + lx * 4;   // zero-filled outside the image by TMA
-            float gf[4];
-            if (p.gt8) {
-                const uchar4 g8 = *reinterpret_cast<const uchar4*>(s_tile + soff);
-                gf[0] = (float)g8.x; gf[1] = (float)g8.y; gf[2] = (float)g8.z; gf[3] = (float)g8.w;
-            } else {
-                const longlong2* sp2 = reinterpret_cast<const longlong2*>(reinterpret_cast<const long long*>(s_tile) + soff);
-                const longlong2 glo = sp2[0], ghi = sp2[1];
-                gf[0] = (float)(int)glo.x; gf[1] = (float)(int)glo.y; gf[2] = (float)(int)ghi.x; gf[3] = (float)(int)ghi.y;
-            }
-            const float cval = taps.class_value(pc);
-            if (outb) {
-                if (vec) __stcs((float4*)(outb + off), make_float4(cval, cval, cval, cval));
-                else
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) outb[off + j] = cval;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float tg = p.nc_pow2 ? __fmul_rn(gf[j], p.inv_nc) : __fdiv_rn(gf[j], ncf);
-                const float d = cval - tg;
-                float l = (KMSE || fabsf(d) < 1.0f) ? d * d : 2.0f * fabsf(d) - 1.0f;
-                if (!SFH_PIX_OK(j)) l = 0.f;
-                loss_sum += l;
-            }
-        }
-        __syncwarp();
-        SFH_TLS(1, 3);
-        if (fits && lane == 0) mbar_arrive(&s_empty[s]);                // stage may be refilled
-
-        // per-pixel path (patch touches a class edge), one pixel at a time as in k_fused
-#pragma unroll 1
-        for (int k = 0; k < kLStash; ++k) {
-            const int q = q0 + k * (kWarps - 1);
-            if (q >= E) break;
-            had_edge = true;
-            const unsigned item = list[q];
-            const int pr = (item & 0xffu) >> 3, pk = item & 7u;
-            const int row = band0 + pr * 8 + ly;
-            const int col = tx * kTileW + pk * kPatchW + lx * 4;
-            const bool row_ok = FT || row < H;
-            const int rowc = FT ? row : min(row, H - 1);
-            const bool vec = FT || (p.vec4 && row_ok && col + 3 < W);
-            const int off = rowc * W + col;
-            float gf[4];
-            if (fits) {
-                unsigned sv = stash[0];
-#pragma unroll
-                for (int kk = 1; kk < kLStash; ++kk) sv = (k == kk) ? stash[kk] : sv;
-                gf[0] = (float)(sv & 0xffu); gf[1] = (float)((sv >> 8) & 0xffu);
-                gf[2] = (float)((sv >> 16) & 0xffu); gf[3] = (float)(sv >> 24);
-            } else {                                                    // stage still held: read the ids again
-                const int soff = (pr * 8 + ly) * kTileW + pk * kPatchW + lx * 4;
-                const longlong2* sp2 = reinterpret_cast<const longlong2*>(reinterpret_cast<const long long*>(s_tile) + soff);
-                const longlong2 glo = sp2[0], ghi = sp2[1];
-                gf[0] = (float)(int)glo.x; gf[1] = (float)(int)glo.y; gf[2] = (float)(int)ghi.x; gf[3] = (float)(int)ghi.y;
-            }
-            float tgt[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tgt[j] = p.nc_pow2 ? __fmul_rn(gf[j], p.inv_nc) : __fdiv_rn(gf[j], ncf);
-            const float v = p.ys ? __ldg(p.ys + rowc) : mesh_coord(rowc, H);
-            float u[4];
-            if (FT && p.xs) {
-                const float4 u4 = __ldg(reinterpret_cast<const float4*>(p.xs + col));
-                u[0] = u4.x; u[1] = u4.y; u[2] = u4.z; u[3] = u4.w;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int cx = min(col + j, W - 1);
-                    u[j] = p.xs ? __ldg(p.xs + cx) : mesh_coord(cx, W);
-                }
-            }
-            float o[4];
-            bool any = false;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const Pix qx = pixel_geom<SFH_MODE_BILINEAR>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]),
-                                                             __fmul_rn(u[j], Hm.h[6]), v, Wc_f, Hc_f);
-                const TapVals tv = taps.fetch4(0, qx.x0, qx.y0);
-                o[j] = bilerp(qx, tv);
-                const float d = o[j] - tgt[j];
-                float l, g;
-                if (KMSE || fabsf(d) < 1.0f) { l = d * d; g = d; }
-                else { l = 2.0f * fabsf(d) - 1.0f; g = d > 0.f ? 1.0f : -1.0f; }
-                if (!SFH_PIX_OK(j)) { l = 0.f; g = 0.f; }
-                loss_sum += l;
-                if (__any_sync(0xffffffffu, !tv.uni)) {
-                    g *= gscale;
-                    const float gix = ((tv.b - tv.a) * qx.sy + (tv.d - tv.c) * qx.ny) * g;
-                    const float giy = ((tv.c - tv.a) * qx.ex + (tv.d - tv.b) * qx.wx) * g;
-                    acc.add(qx, gix, giy, halfWc, halfHc, u[j]);
-                    any = true;
-                }
-            }
-            if (outb) {
-                if (vec) __stcs((float4*)(outb + off), make_float4(o[0], o[1], o[2], o[3]));
-                else
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) outb[off + j] = o[j];
-            }
-            if (any) acc.end_row(v);
-        }
-#undef SFH_PIX_OK
-        if (!fits) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[s]);
-        }
-
-        // ---- this warp's sums of this tile go to the fixed slot (tile, warp) ----
-        float* slot = p.partials + ((size_t)t * kWarps + warp) * kNPart;
-        const float lsum = KMSE ? loss_sum : 0.5f * loss_sum;
-        if (had_edge) {                                                 // warp-uniform
-            float vals[16];
-            vals[0] = lsum;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) vals[1 + k] = acc.a[k];
-#pragma unroll
-            for (int k = 10; k < 16; ++k) vals[k] = 0.f;
-            const float tot = warp_reduce16(vals, lane);
-            const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            if (!(lane & 1) && idx < kNPart) slot[idx] = tot;
-            acc.zero();
-        } else {                                                        // only the loss is non-zero
-            const float tot = warp_sum(lsum);
-            if (lane < kNPart) slot[lane] = lane == 0 ? tot : 0.f;
-        }
-        loss_sum = 0.f;
-
-        SFH_TLS(1, 4); SFH_TLS(0, 7);
-        if (lister) list_finish(i + kLLook, pend, pend_items);
-        // next tile of this CTA
-        t += G;
-        tx += dX;
-        int carry = tx >= tiles_x;
-        tx -= carry * tiles_x;
-        ty += dY + carry;
-        carry = ty >= tiles_y;
-        ty -= carry * tiles_y;
-        b += dB + carry;
+    }
+    // every sample reduced => advance the epoch (the slots of this launch become stale for the next one)
+    if (!counted && threadIdx.x == 0 && atomicAdd(p.counters + p.B, 1) == p.B - 1) {
+        p.counters[p.B] = 0;
+        p.counters[kEpochIdx] = (int)want;
     }
 }
 
-// Second stage of the streaming path: one CTA per sample adds that sample's (tile, warp) slots in
+// Second launch of the training tail: one CTA per sample adds that sample's per-tile partials in
 // fixed order in fp64, then the optional weighting + batch mean + total dtheta (last CTA by ticket).
 constexpr int kFinThreads = 288;                 // 3 float4 columns of a slot x 96 slot lanes
 __global__ void __launch_bounds__(kFinThreads) k_train_finalize(const __grid_constant__ FusedParams p) {
@@ -1409,12 +1200,10 @@ __global__ void k_sat_cols(unsigned* S, int sp, int rows, int cols) {
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 constexpr int64_t kTicketBytes = 262400;   // (65535 + 3) int32 tickets, 256-aligned
 
-// partial slots per sample: k_fused at R = 1 (upper bound over R) or k_train_stream's (tile, warp) slots
+// partial slots per sample: one per CTA tile of k_fused at R = 1 (upper bound over R)
 static int64_t partial_slots(int H, int W) {
     const int64_t tx = (W + kTileW - 1) / kTileW;
-    const int64_t fused = tx * ((H + kWarps - 1) / kWarps);
-    const int64_t stream = tx * ((H + 8 * kLR - 1) / (8 * kLR)) * kWarps;
-    return fused > stream ? fused : stream;
+    return tx * ((H + kWarps - 1) / kWarps);
 }
 
 static int check_template(const sfh_template* t) {
@@ -1446,9 +1235,18 @@ static void fill_common(FusedParams& p, const float* theta, const sfh_template* 
         while (R > 1 && (int64_t)tiles_x * ((H + kWarps * R - 1) / (kWarps * R)) * B < 4 * 3 * 148) R >>= 1;
     p.rows_per_warp = R;
     p.ntiles = tiles_x * ((H + kWarps * R - 1) / (kWarps * R));
+    static const bool no_lean = getenv("SFH_NO_LEAN") != nullptr, no_compact = getenv("SFH_NO_COMPACT") != nullptr;
+    p.lean = no_lean ? 0 : 1;
+    p.compact = no_compact ? 0 : 1;
 }
 
 static inline bool aligned16(const void* q) { return ((uintptr_t)q & 15u) == 0; }
+
+// SFH_TWO_LAUNCH=1: per-sample reductions in a second (programmatically dependent) launch instead of in-kernel
+static bool two_launch() {
+    static const bool v = getenv("SFH_TWO_LAUNCH") != nullptr;
+    return v;
+}
 
 static int setup_ws(FusedParams& p, void* ws, int64_t ws_bytes) {
     const int64_t need = sfh_workspace_bytes(p.B, p.H, p.W);
@@ -1457,7 +1255,9 @@ static int setup_ws(FusedParams& p, void* ws, int64_t ws_bytes) {
     // stay zero between calls, so later calls with another B never read stale contrib/partials as tickets
     p.counters = (int*)ws;                                             // [B+3]: samples, batch, tile ticket, done
     p.contrib = (double*)((char*)ws + kTicketBytes);                   // [B]
-    p.partials = (float*)((char*)p.contrib + align_up((int64_t)p.B * 8, 256));
+    p.partials = (float*)((char*)p.contrib + align_up((int64_t)p.B * 8, 256));    // 8 bytes per value (tagged slots)
+    p.poi.pub = (unsigned long long*)((char*)p.partials + align_up((int64_t)p.B * partial_slots(p.H, p.W) * kNPart * 8, 256));
+    p.poi.epoch = p.counters + kEpochIdx;
     return 0;
 }
 
@@ -1466,11 +1266,15 @@ static int launch_fmt(const FusedParams& p, dim3 grid, size_t dyn, bool ft, cuda
     auto kf = k_fused<FMT, MODE, EPI, true>;
     auto kg = k_fused<FMT, MODE, EPI, false>;
     if (dyn > 32 * 1024) {                     // static (~9 KiB) + dynamic above 48 KiB needs the opt-in
-        static bool raised = false;            // per instantiation; idempotent, so a race is harmless
-        if (!raised) {
+        // the attribute is per device: remember which devices of this process already have it
+        // (per instantiation; setting it twice is harmless, so a race between threads is too)
+        static unsigned long long raised = 0ull;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 64 || !((raised >> dev) & 1ull)) {
             cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8 * kTileW * 8);
             cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8 * kTileW * 8);
-            raised = true;
+            if (dev < 64) raised |= 1ull << dev;
         }
     }
     cudaLaunchConfig_t cfg = {};
@@ -1546,51 +1350,6 @@ static int launch_finalize(const FusedParams& p, cudaStream_t st, int comps = 0)
         return (int)cudaLaunchKernelEx(&cfg, k_comp_finalize, p, 1, 9, p.dtheta, 1.0);
     }
     return (int)cudaLaunchKernelEx(&cfg, k_train_finalize, p);
-}
-
-template <int FMT, bool KMSE>
-static int launch_stream_fmt(const FusedParams& p, bool ft, int sms, size_t dyn, cudaStream_t st) {
-    auto kf = k_train_stream<FMT, true, KMSE>;
-    auto kg = k_train_stream<FMT, false, KMSE>;
-    static size_t raised = 0;                  // per instantiation; idempotent, so a race is harmless
-    static int per_sm = 0;
-    if (dyn > raised || !per_sm) {
-        cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, kThreads, dyn) != cudaSuccess || occ < 1) occ = 1;
-        per_sm = occ;
-        raised = dyn;
-    }
-    const int total = p.ntiles * p.B;
-    const int resident = sms * per_sm;
-    const int ctas = total < resident ? total : resident;
-    if (ft) kf<<<ctas, kThreads, dyn, st>>>(p);
-    else    kg<<<ctas, kThreads, dyn, st>>>(p);
-    const int rc = (int)cudaGetLastError();
-    return rc ? rc : launch_finalize(p, st);
-}
-
-template <int FMT>
-static int launch_stream_kind(const FusedParams& p, bool ft, int sms, size_t dyn, cudaStream_t st) {
-    return p.kind == SFH_LOSS_MSE ? launch_stream_fmt<FMT, true>(p, ft, sms, dyn, st)
-                                  : launch_stream_fmt<FMT, false>(p, ft, sms, dyn, st);
-}
-
-static int launch_stream(const FusedParams& p, cudaStream_t st) {
-    static const int sms = [] {
-        int dev = 0, n = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        return n;
-    }();
-    const bool ft = p.vec4 && (p.W % kTileW == 0) && (p.H % 8 == 0) && (!p.xs || (((uintptr_t)p.xs & 15u) == 0));
-    const size_t dyn = (size_t)kLS * kLStageBytes + (size_t)p.B * 9 * sizeof(float);
-    switch (p.t.fmt) {
-        case SFH_TMPL_F32: return launch_stream_kind<SFH_TMPL_F32>(p, ft, sms, dyn, st);
-        case SFH_TMPL_Q2:  return launch_stream_kind<SFH_TMPL_Q2>(p, ft, sms, dyn, st);
-        case SFH_TMPL_Q4:  return launch_stream_kind<SFH_TMPL_Q4>(p, ft, sms, dyn, st);
-        default: return SFH_E_BADFMT;
-    }
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
@@ -1671,7 +1430,8 @@ const char* sfh_error_string(int code) {
 
 int64_t sfh_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
-    return kTicketBytes + align_up((int64_t)B * 8, 256) + align_up((int64_t)B * partial_slots(H, W) * kNPart * 4, 256);
+    return kTicketBytes + align_up((int64_t)B * 8, 256) + align_up((int64_t)B * partial_slots(H, W) * kNPart * 8, 256) +
+           align_up((int64_t)B * 10 * 8, 256);
 }
 
 int sfh_template_pack(const float* tmpl, int Hc, int Wc, const float* palette_host, int n_palette,
@@ -1712,6 +1472,27 @@ int sfh_warp_fwd(const float* theta, const sfh_template* tmpl, const float* xs, 
     return SFH_E_BADMODE;
 }
 
+int sfh_forward_tail(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
+                     int B, int H, int W, int mode, float* out,
+                     const float* court_poi, int64_t court_poi_bstride, int N, float* poi_out, void* stream) {
+    int rc = check_template(tmpl);
+    if (rc) return rc;
+    if (!theta || !out || B <= 0 || H <= 0 || W <= 0) return SFH_E_BADARG;
+    if (court_poi && (N <= 0 || !poi_out)) return SFH_E_BADARG;
+    FusedParams p;
+    fill_common(p, theta, tmpl, xs, ys, B, H, W);
+    p.out_f = out;
+    p.vec4 = (W % 4 == 0) && aligned16(out);
+    if (court_poi) {
+        p.poi.theta = theta; p.poi.court_poi = court_poi; p.poi.bstride = court_poi_bstride;
+        p.poi.N = N; p.poi.normalize = 1; p.poi.poi_out = poi_out;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == SFH_MODE_BILINEAR) return launch_fused<SFH_MODE_BILINEAR, kEpiStore>(p, st);
+    if (mode == SFH_MODE_NEAREST) return launch_fused<SFH_MODE_NEAREST, kEpiStore>(p, st);
+    return SFH_E_BADMODE;
+}
+
 int sfh_warp_bwd(const float* theta, const sfh_template* tmpl, const float* xs, const float* ys,
                  const float* grad_out, int B, int H, int W, float* dtheta,
                  void* workspace, int64_t workspace_bytes, void* stream) {
@@ -1723,8 +1504,7 @@ int sfh_warp_bwd(const float* theta, const sfh_template* tmpl, const float* xs, 
     if ((rc = setup_ws(p, workspace, workspace_bytes))) return rc;
     p.grad_out = grad_out; p.dtheta = dtheta;
     p.vec4 = (W % 4 == 0) && aligned16(grad_out);
-    static const bool one_launch = getenv("SFH_ONE_LAUNCH") != nullptr;
-    p.split_finalize = one_launch ? 0 : 1;
+    p.split_finalize = two_launch() ? 1 : 0;
     p.fin_slots = p.ntiles;
     rc = launch_fused<SFH_MODE_BILINEAR, kEpiBwd>(p, (cudaStream_t)stream);
     if (rc || !p.split_finalize) return rc;
@@ -1767,24 +1547,10 @@ int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* a
         p.rows_per_warp = 8;
         p.ntiles = ((a->W + kTileW - 1) / kTileW) * ((a->H + 63) / 64);
     }
-    // experimental streaming kernel (persistent tile loop; opt-in until it beats k_fused: measured
-    // 79 us vs 61 us on C2)
-    static const bool use_stream = getenv("SFH_STREAM") != nullptr;
-    if (use_stream && a->B <= kLMaxB) {
-        FusedParams q = p;
-        q.rows_per_warp = kLR;
-        q.ntiles = ((a->W + kTileW - 1) / kTileW) * ((a->H + 8 * kLR - 1) / (8 * kLR));
-        q.fin_slots = q.ntiles * kWarps;
-        if (make_gt_map(q)) {
-            q.use_tma = 1;
-            return launch_stream(q, (cudaStream_t)stream);
-        }
-    }
     p.use_tma = make_gt_map(p) ? 1 : 0;
-    // the per-sample / batch reduction runs as a second, programmatically dependent launch: the
-    // main kernel's CTAs then retire without a ticket (no MEMBAR.GPU per CTA, no serial tail)
-    static const bool one_launch = getenv("SFH_ONE_LAUNCH") != nullptr;
-    p.split_finalize = one_launch ? 0 : 1;
+    // the per-sample / batch reduction runs inside the launch (tagged slots, see k_fused) or, with
+    // SFH_TWO_LAUNCH=1, as a second, programmatically dependent launch
+    p.split_finalize = two_launch() ? 1 : 0;
     p.fin_slots = p.ntiles;
     rc = a->kind == SFH_LOSS_MSE ? launch_fused<SFH_LOSS_MSE, kEpiLoss>(p, (cudaStream_t)stream)
                                  : launch_fused<SFH_LOSS_SMOOTHL1, kEpiLoss>(p, (cudaStream_t)stream);
@@ -1817,8 +1583,7 @@ int sfh_predict_tail(const sfh_template* tmpl, const sfh_predict_tail_args* a, v
         p.poi.N = a->N; p.poi.normalize = 1; p.poi.poi_out = a->poi_out;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    static const bool one_launch = getenv("SFH_ONE_LAUNCH") != nullptr;
-    const bool split = a->score && p.ratio != 0 && !one_launch;      // the score is reduced by k_score_finalize
+    const bool split = a->score && p.ratio != 0 && two_launch();     // the score is reduced by k_comp_finalize
     p.split_finalize = split ? 1 : 0;
     p.fin_slots = p.ntiles;
     if (a->mode == SFH_MODE_NEAREST) rc = launch_fused<SFH_MODE_NEAREST, kEpiPredict>(p, st);

@@ -2,8 +2,8 @@
 
 ``reprojection_loss`` / ``ReprojectionLoss`` (models/losses.py:6-29) run on the sfh kernel and
 are differentiable w.r.t. ``inputs``; ``per_sample_weighted_criterion`` (models/losses.py:33-41)
-keeps the reference's plain-broadcast weighting so the ``[B]*[B,1] -> [B,B]`` quirk
- is preserved when it is fed the fused per-sample losses.
+and its tail ``weight_and_reduce`` keep the reference's plain-broadcast weighting so the
+``[B]*[B,1] -> [B,B]`` quirk is preserved when fed the fused per-sample losses.
 """
 from __future__ import annotations
 
@@ -67,6 +67,17 @@ class ReprojectionLoss(torch.nn.Module):
 
     def forward(self, inputs, targets, nonzeros, num_nonzero, reduction="mean"):
         return reprojection_loss(inputs, targets, nonzeros, num_nonzero, reduction)
+
+
+def per_sample_weighted_criterion(criterion, inputs, targets, per_sample_weights):
+    """models/losses.py:33-41, same signature: ``criterion`` is an ``nn.MSELoss(reduction='none')`` /
+    ``nn.SmoothL1Loss(reduction='none')``-like callable; elementwise loss, mean over (1,2), plain-broadcast
+    weighting (``[B]*[B,1] -> [B,B]`` quirk preserved), batch mean.  Runs on torch ops: it is the generic,
+    unfused form; ``STNWarpStage.train_tail`` fuses it with the warp for the two reference criteria."""
+    loss = criterion(inputs, targets)
+    loss = torch.mean(loss, dim=(1, 2))
+    loss = loss * per_sample_weights
+    return torch.mean(loss)
 
 
 def weight_and_reduce(per_sample_loss, per_sample_weights):
@@ -141,10 +152,9 @@ class _ConsistFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        dl, ctx.dl = ctx.dl, None
-        if dl is None:
+        if ctx.dl is None:                      # logits did not require grad at forward time
             return None, None, None, None
-        return dl.mul_(g.to(torch.float32)), None, None, None      # in place: the buffer is ours
+        return ctx.dl * g.to(torch.float32), None, None, None       # out of place: backward may run twice
 
 
 def consistency_loss(logits, warp_mask, num_classes, consist_lambda=1.0):

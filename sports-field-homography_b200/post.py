@@ -63,7 +63,8 @@ def postprocess_masks(src, mask_type="gray", out_size=None, n_classes=4, out=Non
     ow, oh = (w, h) if out_size is None else (int(out_size[0]), int(out_size[1]))
     src = src.contiguous()
     shape = (B, oh, ow, 3) if mask_type == "rgb" else (B, oh, ow)
-    if out is None or tuple(out.shape) != shape or out.dtype != torch.uint8 or out.device != src.device:
+    if out is None or tuple(out.shape) != shape or out.dtype != torch.uint8 or out.device != src.device \
+            or not out.is_contiguous():
         out = torch.empty(shape, dtype=torch.uint8, device=src.device)
     xo, yo = _table(w, ow, src.device), _table(h, oh, src.device)
     with torch.cuda.device(src.device):

@@ -64,6 +64,59 @@ class _PoiFn(torch.autograd.Function):
         return dth, None, None, None
 
 
+class _ForwardTailFn(torch.autograd.Function):
+    """warp_mask [B,C,H,W] and poi [B,N,2] of Reconstructor.forward (models/reconstructor.py:185-192) in ONE
+    launch; backward -> dtheta through the generic warp backward and the POI backward."""
+
+    @staticmethod
+    def forward(ctx, theta9, stage):
+        B, H, W = theta9.shape[0], stage.height, stage.width
+        tmpl = stage.fresh_template()
+        N = stage.court_poi.shape[1]
+        out = torch.empty((B, tmpl.C, H, W), dtype=torch.float32, device=theta9.device)
+        poi = torch.empty((B, N, 2), dtype=torch.float32, device=theta9.device)
+        xs, ys = stage.warper.grid_factors(theta9.device)
+        shortcut = stage.warper.edge_shortcut
+        with torch.cuda.device(theta9.device):
+            rc = _lib.lib().sfh_forward_tail(theta9.data_ptr(), tmpl.desc(shortcut), xs.data_ptr(), ys.data_ptr(),
+                                             B, H, W, _lib.MODE[stage.mode], out.data_ptr(),
+                                             stage.court_poi.data_ptr(), stage.poi_bstride, N, poi.data_ptr(), _stream())
+        _lib.check(rc, "sfh_forward_tail")
+        ctx.save_for_backward(theta9)
+        ctx.stage, ctx.tmpl, ctx.shortcut = stage, tmpl, shortcut
+        ctx.set_materialize_grads(False)
+        return out, poi
+
+    @staticmethod
+    def backward(ctx, g_mask, g_poi):
+        (theta9,) = ctx.saved_tensors
+        st = ctx.stage
+        B, H, W = theta9.shape[0], st.height, st.width
+        dth = None
+        if g_mask is not None and st.mode == "bilinear":
+            g = g_mask.contiguous()
+            if g.dtype != torch.float32:
+                raise TypeError("grad_out must be float32")
+            dth = torch.empty_like(theta9)
+            xs, ys = st.warper.grid_factors(theta9.device)
+            ws = _WS.get(theta9.device, B, H, W)
+            with torch.cuda.device(theta9.device):
+                rc = _lib.lib().sfh_warp_bwd(theta9.data_ptr(), ctx.tmpl.desc(ctx.shortcut), xs.data_ptr(), ys.data_ptr(),
+                                             g.data_ptr(), B, H, W, dth.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+            _lib.check(rc, "sfh_warp_bwd")
+        if g_poi is not None:
+            extra = torch.empty_like(theta9)
+            with torch.cuda.device(theta9.device):
+                rc = _lib.lib().sfh_poi_bwd(theta9.data_ptr(), st.court_poi.data_ptr(), st.poi_bstride,
+                                            g_poi.contiguous().data_ptr(), B, st.court_poi.shape[1], 1,
+                                            extra.data_ptr(), _stream())
+            _lib.check(rc, "sfh_poi_bwd")
+            dth = extra if dth is None else dth + extra
+        if dth is None:
+            dth = torch.zeros_like(theta9)
+        return dth, None
+
+
 def _launch_train_tail(stage, theta9, gt_masks, kind, want_mask, gt_poi, nonzeros, num_nonzero,
                        weights, rec_lambda, reproj_lambda, out=None):
     """Allocate outputs (or reuse ``out``) and issue the single fused launch.  Returns a dict of
@@ -82,7 +135,8 @@ def _launch_train_tail(stage, theta9, gt_masks, kind, want_mask, gt_poi, nonzero
         if not cond:
             return None
         t = o.get(name)
-        if t is None or tuple(t.shape) != tuple(shape):
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != torch.float32 or t.device != dev \
+                or not t.is_contiguous():
             t = torch.empty(shape, **f32)
             o[name] = t
         return t
@@ -111,7 +165,7 @@ def _launch_train_tail(stage, theta9, gt_masks, kind, want_mask, gt_poi, nonzero
         a.rec_lambda, a.reproj_lambda = float(rec_lambda), float(reproj_lambda)
         a.loss_out, a.dtheta_total = loss.data_ptr(), dtot.data_ptr()
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-    d = stage.template.desc(stage.warper.edge_shortcut)
+    d = stage.fresh_template().desc(stage.warper.edge_shortcut)
     with torch.cuda.device(dev):
         rc = _lib.lib().sfh_warp_loss_fwd_bwd(d, a, _stream())
     _lib.check(rc, "sfh_warp_loss_fwd_bwd")
@@ -187,6 +241,7 @@ class STNWarpStage(torch.nn.Module):
         self.court_img = court_img
         self.warper = HomographyWarper(self.height, self.width, mode=self.mode, grid_source=grid_source, exact=exact)
         self.template: CourtTemplate = self.warper.set_template(court_img)
+        self._staged_key = self._template_key(court_img)
         self.device = court_img.device
         if court_poi is not None:
             court_poi = _check_f32_cuda(court_poi, "court_poi", self.device)
@@ -194,6 +249,18 @@ class STNWarpStage(torch.nn.Module):
                 raise ValueError(f"court_poi must be [B,N,2], got {tuple(court_poi.shape)}")
         self.court_poi = court_poi
         self.poi_bstride = 0 if court_poi is None or court_poi.shape[0] == 1 else court_poi.shape[1] * 2
+
+    @staticmethod
+    def _template_key(court_img):
+        return (court_img.data_ptr(), court_img._version, tuple(court_img.shape))
+
+    def fresh_template(self) -> CourtTemplate:
+        """The packed template of ``self.court_img``, re-staged if the tensor was modified in place or
+        swapped since it was packed (the fused tails sample the packed copy, not the live tensor)."""
+        if self._template_key(self.court_img) != self._staged_key:
+            self.template = self.warper.set_template(self.court_img)
+            self._staged_key = self._template_key(self.court_img)
+        return self.template
 
     # ------------------------------------------------------------------ reference-named methods
     def warp(self, theta: torch.Tensor, court_img: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -218,18 +285,26 @@ class STNWarpStage(torch.nn.Module):
         return _PoiFn.apply(theta9, poi, bstride, normalize)
 
     def forward_tail(self, theta: torch.Tensor) -> dict:
-        """Warp-stage part of Reconstructor.forward (models/reconstructor.py:185-192)."""
+        """Warp-stage part of Reconstructor.forward (models/reconstructor.py:185-192): ``poi`` and
+        ``warp_mask`` come out of ONE launch (``sfh_forward_tail``), both differentiable w.r.t. theta."""
         ret = {"theta": theta}
-        if self.court_poi is not None:
-            ret["poi"] = self.transform_poi(theta)
-        ret["warp_mask"] = self.warp(theta)
+        if self.court_poi is None:
+            ret["warp_mask"] = self.warp(theta)
+            return ret
+        theta9 = check_theta(theta, self.device)
+        if self.poi_bstride and self.court_poi.shape[0] < theta9.shape[0]:
+            raise ValueError("batch larger than the number of court_poi rows")
+        mask, poi = _ForwardTailFn.apply(theta9, self)
+        ret["poi"] = poi
+        ret["warp_mask"] = mask.squeeze(1)
         return ret
 
     forward = forward_tail
 
     def _buf(self, out, name, shape, dtype):
         t = None if out is None else out.get(name)
-        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != self.device \
+                or not t.is_contiguous():
             t = torch.empty(shape, dtype=dtype, device=self.device)
             if out is not None:
                 out[name] = t
@@ -272,7 +347,10 @@ class STNWarpStage(torch.nn.Module):
         if want_poi:
             a.court_poi, a.court_poi_bstride, a.poi_out = self.court_poi.data_ptr(), self.poi_bstride, poi.data_ptr()
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-        d = self.template.desc(self.warper.edge_shortcut)
+        # integer masks: the edge-free shortcut writes trunc(class_value * nc), which is what the reference
+        # yields for 'nearest'; ATen's bilinear interpolation of a constant region can come out one ulp
+        # low (0.74999994 * 4 -> class 2), so bilinear integer masks always take the exact per-pixel path
+        d = self.fresh_template().desc(self.mode == "nearest")
         with torch.cuda.device(self.device):
             rc = _lib.lib().sfh_predict_tail(d, a, _stream())
         _lib.check(rc, "sfh_predict_tail")
@@ -389,13 +467,15 @@ def patch_reconstructor(net, court_img: Optional[torch.Tensor] = None,
     """Swap the warp stage of a reference ``Reconstructor`` instance for the B200 kernels.
 
     ``net.warp`` / ``net.transform_poi`` keep their signatures (models/reconstructor.py:109,120);
-    ``net.predict`` keeps its signature and result dict (:196-247) but runs the fused tail.  No
-    parameter or buffer is registered, so checkpoints keep loading with strict=True."""
+    ``net.forward`` / ``net.predict`` keep their signatures and result dicts (:160-194, :196-247) but run
+    the fused tails.  No parameter or buffer is registered, so checkpoints keep loading with strict=True."""
     court_img = net.court_img if court_img is None else court_img
     court_poi = net.court_poi if court_poi is None else court_poi
     w = net.warper
+    # exact=True: a drop-in must give train.py's `(warp_mask * nc).long()` consistency targets the
+    # reference's bits; the edge-free shortcut (within 2 ulp) is the opt-in of the fused STNWarpStage API
     stage = STNWarpStage(court_img, court_poi, warp_size=(w.width, w.height),
-                         mask_classes=net.mask_classes, warp_with_nearest=(w.mode == "nearest"))
+                         mask_classes=net.mask_classes, warp_with_nearest=(w.mode == "nearest"), exact=True)
     object.__setattr__(net, "_sfh_stage", stage)      # bypass nn.Module registration
 
     def warp(self, theta, court_img):
@@ -404,21 +484,47 @@ def patch_reconstructor(net, court_img: Optional[torch.Tensor] = None,
     def transform_poi(self, theta, court_poi, normalize=True):
         return stage.transform_poi(theta, court_poi, normalize)
 
+    def resnet_in(self, x, ret):
+        # the reference's Input enum (models/reconstructor.py:9-13), matched by member name so that this
+        # module does not import the reference tree
+        kind = getattr(self.resnet_input, "name", self.resnet_input)
+        if kind == "IMG":
+            return x
+        if kind == "MASK":
+            return ret["logits"]
+        if kind == "IMG_AND_MASK":
+            return torch.cat((ret["logits"], x), 1)
+        if kind == "IMG_AND_MASK_AND_UV" and "uv" in ret:
+            return torch.cat((ret["logits"], x, ret["uv"]), 1)
+        raise NotImplementedError
+
+    def forward(self, x):
+        """Reconstructor.forward (models/reconstructor.py:160-194) with the warp-stage tail in one launch."""
+        ret = {}
+        if self.use_unet:
+            ret["logits"], _, uv = self.forward_unet(x)
+            if uv is not None:
+                ret["uv"] = uv
+        if self.use_resnet:
+            theta = self.resnet_reg(resnet_in(self, x, ret))
+            if self.warper is not None:
+                tail = stage.forward_tail(theta)
+                ret["theta"], ret["poi"], ret["warp_mask"] = theta, tail["poi"], tail["warp_mask"]
+            else:
+                ret["poi"] = stage.transform_poi(theta, None)
+                ret["theta"] = theta
+        return ret
+
     def predict(self, x, consistency=True, project_poi=False):
+        """Reconstructor.predict (models/reconstructor.py:196-247) with the fused predict tail."""
         ret = {}
         if self.use_unet:
             ret["logits"], _, _ = self.forward_unet(x)
         if self.use_resnet:
-            from models.reconstructor import Input   # the reference's own enum
-            if self.resnet_input == Input.IMG:
-                y = x
-            elif self.resnet_input == Input.MASK:
-                y = ret["logits"]
-            elif self.resnet_input == Input.IMG_AND_MASK:
-                y = torch.cat((ret["logits"], x), 1)
-            else:
-                raise NotImplementedError
-            theta = self.resnet_reg(y)
+            kind = getattr(self.resnet_input, "name", self.resnet_input)
+            if kind == "IMG_AND_MASK_AND_UV":
+                raise NotImplementedError             # as the reference's predict (:216-217)
+            theta = self.resnet_reg(resnet_in(self, x, ret))
             ret["theta"] = theta
             if self.warper is not None:
                 tail = stage.predict_tail(theta, ret.get("logits") if (consistency and self.use_unet) else None,
@@ -433,4 +539,6 @@ def patch_reconstructor(net, court_img: Optional[torch.Tensor] = None,
     net.warp = types.MethodType(warp, net)
     net.transform_poi = types.MethodType(transform_poi, net)
     net.predict = types.MethodType(predict, net)
+    if court_poi is not None:
+        net.forward = types.MethodType(forward, net)      # poi + warp_mask from one launch
     return stage

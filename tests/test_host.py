@@ -42,12 +42,14 @@ def test_abi_metadata_and_argument_errors_without_gpu():
     assert b"sm_100a" in l.sfh_build_info()
     assert l.sfh_error_string(0) == b"success"
     assert b"workspace" in l.sfh_error_string(-4)
-    # workspace size is pure host arithmetic: a fixed 262400-byte ticket area, B doubles (256-aligned),
-    # 12 floats per partial slot (max of one per 128x8 tile / 8 per 128x32 tile of the streaming kernel)
-    assert l.sfh_workspace_bytes(64, 360, 640) == 262400 + 512 + 64 * max(5 * 45, 5 * 12 * 8) * 12 * 4
+    # workspace size is pure host arithmetic: a fixed 262400-byte ticket / epoch area, B doubles (256-aligned),
+    # 12 tagged 8-byte words per partial slot (one slot per 128x8 tile: the upper bound over tile heights),
+    # 10 tagged words per sample for the POI block (256-aligned)
+    assert l.sfh_workspace_bytes(64, 360, 640) == 262400 + 512 + 64 * (5 * 45) * 12 * 8 + 64 * 10 * 8
     assert l.sfh_workspace_bytes(0, 360, 640) == 0
     # argument validation happens before any CUDA call
     assert l.sfh_warp_fwd(None, None, None, None, 1, 1, 1, 0, None, None) < 0
+    assert l.sfh_forward_tail(None, None, None, None, 1, 1, 1, 0, None, None, 0, 0, None, None) < 0
     assert l.sfh_warp_loss_fwd_bwd(None, None, None) < 0 and l.sfh_predict_tail(None, None, None) < 0
     assert l.sfh_poi_fwd(None, None, 0, 1, 1, 1, None, None) == -1
     assert l.sfh_transform_points_fwd(None, 1, None, 2, 3, None, None) == -1

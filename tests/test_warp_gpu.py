@@ -512,10 +512,10 @@ def test_workspace_reuse_across_batch_sizes():
 
 
 def test_alternative_launch_paths_agree():
-    """The training tail has three launch shapes (selected per process by environment variables):
-    k_fused + k_train_finalize (default), k_fused alone with in-kernel tickets (SFH_ONE_LAUNCH) and the
-    experimental persistent tile loop (SFH_STREAM).  They must give the same warp mask bit for bit and
-    the same sums up to fp32 summation order."""
+    """The fused tails have two launch shapes (selected per process by an environment variable): k_fused alone
+    with the in-launch tagged-slot reduction (default) and k_fused + k_train_finalize / k_comp_finalize as a
+    programmatically dependent second launch (SFH_TWO_LAUNCH).  They must give the same warp mask bit for
+    bit and the same sums up to fp32 summation order."""
     import subprocess
     import sys
     code = r"""
@@ -553,13 +553,13 @@ for (W, H, B, kind) in [(640, 360, 9, 'MSE'), (200, 77, 5, 'SmoothL1'), (1280, 7
 print('RESULT' + json.dumps(out))
 """ % ROOT
     res = {}
-    for name, env in (("default", {}), ("one_launch", {"SFH_ONE_LAUNCH": "1"}), ("stream", {"SFH_STREAM": "1"})):
+    for name, env in (("default", {}), ("two_launch", {"SFH_TWO_LAUNCH": "1"})):
         e = dict(os.environ)
         e.update(env)
         pr = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
         assert pr.returncode == 0, pr.stderr[-2000:]
         res[name] = json.loads([l for l in pr.stdout.splitlines() if l.startswith("RESULT")][0][6:])
-    for name in ("one_launch", "stream"):
+    for name in ("two_launch",):
         for cfg, a in res["default"].items():
             b = res[name][cfg]
             assert a["mask"] == b["mask"] and a["mask_sq"] == b["mask_sq"], (name, cfg)
@@ -567,7 +567,7 @@ print('RESULT' + json.dumps(out))
             np.testing.assert_allclose(b["rec"], a["rec"], rtol=1e-6, atol=1e-9)
             assert a["pmask"] == b["pmask"]
             np.testing.assert_allclose(b["gbwd"], a["gbwd"], rtol=0, atol=1e-5 * max(abs(x) for x in a["gbwd"]))   # generic backward
-            np.testing.assert_allclose(b["score"], a["score"], rtol=1e-6)     # predict tail: score by k_score_finalize vs tickets
+            np.testing.assert_allclose(b["score"], a["score"], rtol=1e-6)     # predict tail: score by k_comp_finalize vs in-launch
             scale = max(abs(x) for x in a["dth"])
             np.testing.assert_allclose(b["dth"], a["dth"], rtol=0, atol=1e-5 * scale)
 
@@ -754,6 +754,69 @@ def test_frame_court_mapping_matches_cv2_perspective_transform():
 
 
 # ---------------------------------------------------------------------- API / error conventions
+# ------------------------------------------------------- large-batch tile shapes (R = 16, 64 KB TMA boxes)
+def test_c4_full_batch_matches_oracle():
+    """C4 at its stated batch (pitch template, 1280x720, B=32 -> tile height R=16): bilinear forward + POI through
+    the one-launch forward tail, against the C oracle (production mode: edge-free patches as constants <= 2 ulp)."""
+    W, H, B = 1280, 720, 32
+    tmpl, poi = sfh_b200.load_bundled("pitch_v3_nc4", (W, H), 4, 1)
+    th = synth.theta_family_b(B, 41)
+    ref = co.warp_fwd(th.numpy(), tmpl.numpy(), H, W)[:, 0]
+    p64 = co.poi_fwd(th.numpy(), poi.expand(B, -1, -1).numpy())
+    for exact in (True, False):
+        st = mk_stage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, exact=exact)
+        r = st.forward_tail(th.to(DEV))
+        assert set(r) == {"theta", "poi", "warp_mask"}
+        assert np.abs(r["warp_mask"].cpu().numpy() - ref).max() <= TOL_MASK, exact
+        assert np.abs(r["poi"].cpu().numpy() - p64).max() * W <= TOL_POI_PX
+        # the one-launch tail equals the two separate calls bit for bit
+        assert torch.equal(r["warp_mask"], st.warp(th.to(DEV)))
+        assert torch.equal(r["poi"], st.transform_poi(th.to(DEV)))
+
+
+def test_c5_micro_batch_matches_oracle():
+    """C5's micro-batch (256 frames of 1280x720, nearest + CE score + POI: R=16 tiles, 64 KB logits TMA box, short
+    bottom tiles remapped to extra z-slices at B=256): a strided sample of 16 frames is compared with the C oracle,
+    the rest through the batch-split property (a frame's result does not depend on its batch)."""
+    W, H, B = 1280, 720, 256
+    tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (W, H), 4, 1)
+    th = synth.theta_family_b(B, 55)
+    g = torch.Generator(device=DEV).manual_seed(12)
+    logits = torch.randn(B, 4, 360, 640, generator=g, device=DEV)
+    st = mk_stage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, warp_with_nearest=True)
+    r = st.predict_tail(th.to(DEV), logits, consistency=True, project_poi=True)
+    idx = list(range(3, B, 16))
+    assert len(idx) == 16
+    ths = th[idx]
+    m_ref, s_ref = co.predict_tail(ths.numpy(), tmpl.numpy(), logits[idx].cpu().numpy(), 4, H, W, "nearest")
+    assert np.array_equal(r["warp_mask"][idx].cpu().numpy(), m_ref)
+    np.testing.assert_allclose(r["consist_score"][idx].cpu().numpy(), s_ref, rtol=1e-5)
+    p64 = co.poi_fwd(ths.numpy(), poi.expand(len(idx), -1, -1).numpy())
+    assert np.abs(r["poi"][idx].cpu().numpy() - p64).max() * W <= TOL_POI_PX
+    # every frame: same mask and score (to summation order: tile shapes differ with B) as in a 15-frame batch (C3's shape)
+    for lo in (0, 120, 241):
+        sub = st.predict_tail(th[lo:lo + 15].to(DEV), logits[lo:lo + 15].contiguous(), consistency=True, project_poi=True)
+        assert torch.equal(sub["warp_mask"], r["warp_mask"][lo:lo + 15])
+        assert torch.equal(sub["poi"], r["poi"][lo:lo + 15])
+        torch.testing.assert_close(sub["consist_score"], r["consist_score"][lo:lo + 15], rtol=1e-5, atol=0)
+
+
+def test_predict_tail_bilinear_int_masks_match_oracle_in_production_mode():
+    """A bilinear warper's integer masks / consistency targets must not take the edge-free shortcut: ATen's
+    interpolation of a constant region is often one ulp low (0.74999994 * 4 -> class 2), so trunc(constant * nc)
+    would flip whole classes.  Default stage (exact=False) vs the oracle, bit for bit."""
+    W, H, B = 640, 360, 6
+    tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (W, H), 4, 1)
+    th = synth.theta_family_a(B, 31)
+    logits = torch.randn(B, 4, H // 2, W // 2, generator=torch.Generator().manual_seed(2))
+    m_ref, s_ref = co.predict_tail(th.numpy(), tmpl.numpy(), logits.numpy(), 4, H, W, "bilinear")
+    st = sfh_b200.STNWarpStage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, grid_source="cpu")      # exact=False default
+    r = st.predict_tail(th.to(DEV), logits.to(DEV), consistency=True, project_poi=False)
+    assert np.array_equal(r["warp_mask"].cpu().numpy(), m_ref), (r["warp_mask"].cpu().numpy() != m_ref).mean()
+    np.testing.assert_allclose(r["consist_score"].cpu().numpy(), s_ref, rtol=1e-5)
+
+
+
 def test_error_conventions_and_state_dict():
     tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 2)
     st = mk_stage(tmpl.to(DEV), poi.to(DEV), (640, 360), 4)
@@ -776,14 +839,82 @@ def test_error_conventions_and_state_dict():
 
 
 class _FakeNet(torch.nn.Module):
-    """The attributes patch_reconstructor touches on a reference Reconstructor."""
+    """The attributes patch_reconstructor touches on a reference Reconstructor, plus stand-ins for the trunk:
+    ``forward_unet`` returns fixed logits and ``resnet_reg`` fixed thetas (the conv trunk is out of scope), so the
+    patched ``forward`` / ``predict`` can be run and diffed against the restated reference tails."""
 
-    def __init__(self, court_img, court_poi, size, nearest):
+    class _In:
+        name = "MASK"                   # models/reconstructor.py:9-13 Input.MASK
+
+    def __init__(self, court_img, court_poi, size, nearest, logits=None, theta=None):
         super().__init__()
         self.court_img, self.court_poi = court_img, court_poi
-        self.mask_classes, self.use_unet, self.use_resnet = 4, False, False
+        self.mask_classes = 4
+        self.use_unet, self.use_resnet = logits is not None, theta is not None
+        self.resnet_input = self._In()
+        self._logits, self._theta = logits, theta
         self.warper = kr.HomographyWarper(size[1], size[0], mode="nearest" if nearest else "bilinear")
         self.reg = torch.nn.Linear(2, 2)
+
+    def forward_unet(self, x):
+        return self._logits, None, None
+
+    def resnet_reg(self, y):
+        assert y is self._logits        # Input.MASK feeds the logits
+        return self._theta
+
+    def warp(self, theta, court_img):   # models/reconstructor.py:109-118
+        return self.warper(court_img[0:theta.shape[0]], theta).squeeze(1)
+
+    def transform_poi(self, theta, court_poi, normalize=True):      # :120-130
+        return kr.transform_poi(theta, court_poi, normalize)
+
+
+@pytest.mark.parametrize("nearest,W,H", [(True, 1280, 720), (False, 640, 360)])
+def test_patched_forward_and_predict_match_the_reference_tails(nearest, W, H):
+    """patch_reconstructor's replacements of Reconstructor.forward (:160-194) and .predict (:196-247) are executed
+    on a stand-in net and diffed key by key (names, dtypes, shapes, values) against the restated reference run
+    on the same device (what the reference really executes on a GPU box)."""
+    B = 5
+    tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (W, H), 4, B)
+    th = synth.theta_family_b(B, 9).to(DEV)
+    logits = torch.randn(B, 4, 360, 640, generator=torch.Generator().manual_seed(6)).to(DEV)
+    x = torch.zeros(B, 3, 8, 8, device=DEV)
+    net = _FakeNet(tmpl.to(DEV), poi.to(DEV), (W, H), nearest, logits, th).to(DEV)
+    with torch.no_grad():
+        ref_fwd = {"logits": logits, "theta": th, "poi": net.transform_poi(th, net.court_poi),
+                   "warp_mask": net.warp(th, net.court_img)}                                   # :185-192
+        ref_pred = kr.predict_tail(th, net.court_img, logits, net.court_poi, 4, H, W,
+                                   "nearest" if nearest else "bilinear", True, True)            # :221-245
+    stage = sfh_b200.patch_reconstructor(net)
+    stage.warper.grid_source = "device"
+    with torch.no_grad():
+        got_fwd = net(x)
+        got_pred = net.predict(x, consistency=True, project_poi=True)
+        got_min = net.predict(x, consistency=False, project_poi=False)
+    assert list(got_fwd) == ["logits", "theta", "poi", "warp_mask"]                            # insertion order of :160-194
+    assert set(got_pred) == {"logits", "theta", "warp_mask", "consist_score", "poi"}
+    assert set(got_min) == {"logits", "theta", "warp_mask"}
+    for k in ("poi", "warp_mask"):
+        assert got_fwd[k].shape == ref_fwd[k].shape and got_fwd[k].dtype == ref_fwd[k].dtype
+    assert float((got_fwd["warp_mask"] - ref_fwd["warp_mask"]).abs().max()) <= (0.0 if nearest else TOL_MASK)
+    assert float((got_fwd["poi"] - ref_fwd["poi"]).abs().max()) * W <= 2e-3 * W / 64   # the reference's own fp32 LU noise
+    assert got_pred["warp_mask"].dtype == torch.int32 and got_pred["warp_mask"].shape == (B, H, W)
+    assert torch.equal(got_pred["warp_mask"], ref_pred["warp_mask"])
+    assert got_pred["consist_score"].shape == (B,) and got_pred["consist_score"].dtype == torch.float32
+    torch.testing.assert_close(got_pred["consist_score"], ref_pred["consist_score"], rtol=1e-5, atol=0)
+    assert float((got_pred["poi"] - ref_pred["poi"]).abs().max()) * W <= 2e-3 * W / 64
+    assert torch.equal(got_min["warp_mask"], got_pred["warp_mask"])
+    assert got_pred["theta"] is th and got_pred["logits"] is logits
+    # gradients flow through the patched forward (train.py:235): d(sum warp + sum poi)/dtheta vs autograd of the restatement
+    if not nearest:
+        t1 = th.clone().requires_grad_(True)
+        net._theta = t1
+        r = net(x)
+        (r["warp_mask"].sum() + r["poi"].sum()).backward()
+        t2 = th.clone().requires_grad_(True)
+        (kr.warp(t2, net.court_img, H, W).sum() + kr.transform_poi(t2, net.court_poi).sum()).backward()
+        assert relnorm(t1.grad.cpu().numpy(), t2.grad.cpu().numpy()).max() <= 2e-3    # fp32 autograd noise floor (SURVEY §7.1)
 
 
 def test_patch_reconstructor_keeps_signatures_and_state_dict():
