@@ -231,6 +231,14 @@ int sfh_consist_loss_fwd_bwd(const float* warp_mask, const float* logits, int B,
                              float lambda, float* loss_out, float* dlogits,
                              void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same pass with the reference's other consistency criterion — train.py:133-134:
+ *   kornia.losses.FocalLoss(alpha=1.0, gamma=2.0, reduction='mean')(logits, (warp_mask * nc).long()) * lambda
+ * following kornia 0.5.x/0.6.x focal_loss including its eps conventions: probabilities softmax + 1e-8, one-hot
+ * targets + 1e-6 (kornia.utils.one_hot), loss_px = sum_c t_c * (-alpha (1 - p_c)^gamma log p_c).  gamma >= 0. */
+int sfh_consist_focal_fwd_bwd(const float* warp_mask, const float* logits, int B, int nc, int H, int W,
+                              float alpha, float gamma, float lambda, float* loss_out, float* dlogits,
+                              void* workspace, int64_t workspace_bytes, void* stream);
+
 /* GPU post-processing of the predict outputs, done BEFORE the device->host copy:
  *   src_kind LOGITS:   [B,nc,h,w] fp32 -> class ids by argmax (utils/postprocess.py:7-18 preds_to_masks;
  *                      argmax(softmax(l)) == argmax(l), first maximum wins)
@@ -251,6 +259,23 @@ int sfh_consist_loss_fwd_bwd(const float* warp_mask, const float* logits, int B,
 int sfh_postprocess(const void* src, int src_kind, int B, int nc, int h, int w,
                     int mask_type, const int* x_ofs, const int* y_ofs, int oh, int ow,
                     unsigned char* out, void* stream);
+
+/* utils/transform.py:7-20 — Warper.warp(theta, proj): kornia HomographyWarper(mode='nearest',
+ * normalized_coordinates=True) on a DOUBLE-precision multi-channel image.
+ * theta [B,3,3] fp64 (output-frame -> template, normalised, as everywhere in this header), tmpl [Bt,C,Hc,Wc] fp64
+ * (tmpl_batch_stride elements between samples, 0 = shared), xs[W] / ys[H] the fp64 meshgrid factors (required: which
+ * dtype kornia builds them in is version dependent, so the caller states it), out [B,C,H,W] fp64.  Coordinates in
+ * fp64 in kornia's operation order, nearbyint pick, zeros outside. */
+int sfh_warp_nearest_f64(const double* theta, const double* tmpl, int64_t tmpl_batch_stride, const double* xs,
+                         const double* ys, int B, int C, int Hc, int Wc, int H, int W, double* out, void* stream);
+
+/* dataset_utils/football_dataset.ipynb cell 11 with preparation.py:129-137 (rescale_theta) — the dataset's mask /
+ * UV-map rendering: cv2.warpPerspective(src, M, (W,H), flags=cv2.INTER_NEAREST), border constant 0, for B matrices
+ * at once.  minv [B,3,3] fp64 = inverse of each M (destination pixel -> source pixel; cv2 inverts M itself),
+ * src [Hs,Ws] pixels of pixel_bytes bytes each (channels interleaved like a cv::Mat; 1,2,3,4,8,16 or 24 bytes),
+ * dst [B,H,W] pixels.  OpenCV's evaluation order (64-column blocks, double precision) and cvRound are reproduced. */
+int sfh_warp_perspective_nearest(const double* minv, int B, const void* src, int Hs, int Ws, int pixel_bytes,
+                                 int H, int W, void* dst, void* stream);
 
 /* Diagnostic: exhaustively compares the kernels' fast correctly-rounded reciprocal with IEEE
  * rcp.rn over every fp32 value with |z| in (1e-8, 1e37) (the range it is used on; the warp path

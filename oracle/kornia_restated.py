@@ -91,16 +91,20 @@ class HomographyWarper(torch.nn.Module):
     """Restated kornia.geometry.transform.HomographyWarper (normalized_coordinates=True)."""
 
     def __init__(self, height: int, width: int, mode: str = "bilinear", padding_mode: str = "zeros",
-                 normalized_coordinates: bool = True, align_corners: bool = False) -> None:
+                 normalized_coordinates: bool = True, align_corners: bool = False, grid_dtype=None) -> None:
         super().__init__()
         self.width, self.height = width, height
         self.mode, self.padding_mode = mode, padding_mode
         self.normalized_coordinates = normalized_coordinates
         self.align_corners = align_corners
+        # kornia 0.5.x creates the grid in __init__ with the default dtype (fp32) and casts it to the homography's
+        # dtype in warp_grid (`grid.to(src_homo_dst)`); later versions build it from the input.  For fp32 inputs the
+        # two coincide; for the fp64 Warper of utils/transform.py the choice is stated by the caller (None = input dtype).
+        self.grid_dtype = grid_dtype
 
     def flow(self, patch_src: torch.Tensor, src_homo_dst: torch.Tensor) -> torch.Tensor:
         grid = create_meshgrid(self.height, self.width, self.normalized_coordinates,
-                               device=patch_src.device, dtype=patch_src.dtype)
+                               device=patch_src.device, dtype=self.grid_dtype or patch_src.dtype)
         return warp_grid(grid, src_homo_dst)
 
     def forward(self, patch_src: torch.Tensor, src_homo_dst: torch.Tensor) -> torch.Tensor:
@@ -179,6 +183,41 @@ def rec_loss_per_sample(warp_mask, gt_masks, mask_classes: int, kind: str = "MSE
     else:
         raise NotImplementedError(kind)
     return torch.mean(ell, dim=(1, 2))
+
+
+def one_hot(labels: torch.Tensor, num_classes: int, dtype=None, eps: float = 1e-6) -> torch.Tensor:
+    """kornia.utils.one_hot (0.5.x/0.6.x): scatter 1.0 along dim 1, then ``+ eps``."""
+    shape = labels.shape
+    oh = torch.zeros((shape[0], num_classes) + tuple(shape[1:]), device=labels.device, dtype=dtype)
+    return oh.scatter_(1, labels.unsqueeze(1), 1.0) + eps
+
+
+def focal_loss(input: torch.Tensor, target: torch.Tensor, alpha: float, gamma: float = 2.0,
+               reduction: str = "none", eps: float = 1e-8) -> torch.Tensor:
+    """kornia.losses.focal_loss as published in kornia 0.5.x/0.6.x (the versions torch 1.8.1 admits,
+    requirements.txt:1,5) — used by train.py:106,134 as FocalLoss(alpha=1.0, gamma=2.0, ...).
+    softmax + eps, one-hot targets carrying kornia.utils.one_hot's own eps, plain log."""
+    input_soft = F.softmax(input, dim=1) + eps
+    target_one_hot = one_hot(target, num_classes=input.shape[1], dtype=input.dtype)
+    weight = torch.pow(-input_soft + 1.0, gamma)
+    focal = -alpha * weight * torch.log(input_soft)
+    loss_tmp = torch.sum(target_one_hot * focal, dim=1)
+    if reduction == "none":
+        return loss_tmp
+    if reduction == "mean":
+        return torch.mean(loss_tmp)
+    if reduction == "sum":
+        return torch.sum(loss_tmp)
+    raise NotImplementedError(reduction)
+
+
+def consistency_loss_focal(logits, warp_mask, num_classes: int, consist_lambda: float = 1.0,
+                           alpha: float = 1.0, gamma: float = 2.0):
+    """train.py:133-134 + 219-223 with ``--consist_loss focal``."""
+    rec_masks_int = (warp_mask * num_classes).to(dtype=torch.long)
+    if rec_masks_int.ndim == 4:
+        rec_masks_int = rec_masks_int[:, 0]
+    return focal_loss(logits, rec_masks_int, alpha, gamma, "mean") * consist_lambda
 
 
 def consistency_loss(logits, warp_mask, num_classes: int, consist_lambda: float = 1.0):

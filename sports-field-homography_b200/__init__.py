@@ -14,6 +14,7 @@ from .losses import (ReprojectionLoss, consistency_loss, consistency_step, per_s
 from .mapping import map_court_to_frame, map_frame_to_court
 from .post import cv2_nearest_table, postprocess_masks
 from .stage import STNWarpStage, patch_reconstructor
+from .tooling import Warper, rescale_theta, warp_perspective_nearest
 from .warper import HomographyWarper, meshgrid_factors, transform_points
 
 __all__ = [
@@ -22,7 +23,7 @@ __all__ = [
     "reprojection_loss", "reprojection_per_sample", "ReprojectionLoss", "weight_and_reduce",
     "per_sample_weighted_criterion",
     "consistency_loss", "consistency_step", "postprocess_masks", "cv2_nearest_table",
-    "map_frame_to_court", "map_court_to_frame",
+    "map_frame_to_court", "map_court_to_frame", "Warper", "warp_perspective_nearest", "rescale_theta",
     "shard_range", "reduce_sums", "global_means",
 ]
 __version__ = "0.1.0"

@@ -14,7 +14,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("SFH_LIB_PATH") or os.path.join(_HERE, "libsfh_b200.so")   # override: development A/B only
-CSRC = [os.path.join(_HERE, "csrc", f) for f in ("sfh_warp.cu", "sfh_poi.cu", "sfh_consist.cu", "sfh_post.cu")]
+CSRC = [os.path.join(_HERE, "csrc", f) for f in ("sfh_warp.cu", "sfh_poi.cu", "sfh_consist.cu", "sfh_post.cu", "sfh_aux.cu")]
 HDRS = [os.path.join(_HERE, "csrc", f) for f in ("sfh_device.cuh", "sfh_poi.cuh")] + \
        [os.path.join(_ROOT, "include", "sfh_b200.h")]
 
@@ -80,7 +80,10 @@ SIGNATURES = {
     "sfh_reproj_loss": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "sfh_consist_workspace_bytes": (_L, []),
     "sfh_consist_loss_fwd_bwd": (_I, [_P, _P, _I, _I, _I, _I, C.c_float, _P, _P, _P, _L, _P]),
+    "sfh_consist_focal_fwd_bwd": (_I, [_P, _P, _I, _I, _I, _I, C.c_float, C.c_float, C.c_float, _P, _P, _P, _L, _P]),
     "sfh_postprocess": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
+    "sfh_warp_nearest_f64": (_I, [_P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "sfh_warp_perspective_nearest": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     "sfh_selftest_rcp": (_I, [_P, _P]),
     "sfh_debug_stream_cast": (_I, [_P, _P, _L, _I, _P]),
 }

@@ -11,6 +11,12 @@
 // lambda / (B*H*W) (reduction 'mean').  exp/log run on the MUFU ex2/lg2 units (rel. error ~1e-7
 // on the probabilities; tests hold loss to 1e-5 relative and gradients to 1e-6 of their scale).
 //
+// Focal variant (train.py:133-134: kornia.losses.FocalLoss(alpha=1.0, gamma=2.0, reduction='mean') as the
+// consistency criterion), restated from kornia 0.5.x/0.6.x focal_loss — eps conventions included:
+//   p~_c = softmax_c + 1e-8;  t_c = [c == cls] + 1e-6 (kornia.utils.one_hot adds its own eps);
+//   loss_px = sum_c t_c * (-alpha * (1 - p~_c)^gamma * log p~_c);  mean over all pixels
+//   dloss_px/dl_k = p_k * (g_k - sum_c g_c p_c),  g_c = t_c * alpha * (gamma (1-p~_c)^(gamma-1) log p~_c - (1-p~_c)^gamma / p~_c)
+//
 // The loss is reduced without data atomics: thread -> warp shuffle -> CTA -> one fp32 partial per
 // CTA; the last CTA (release ticket) adds the partials in fixed order in fp64.  The grid size is a
 // function of the problem size only, so results are run-to-run deterministic.
@@ -36,7 +42,36 @@ struct ConsistParams {
     long long total_px;     // B * plane
     float ncf, lambda, gscale;   // gscale = lambda / total_px
     int nc;
+    int kind;               // 0: cross entropy, 1: focal (kornia 0.5.x focal_loss)
+    float alpha, gamma;     // focal parameters
 };
+
+constexpr float kFocalEpsP = 1e-8f;     // kornia focal_loss: softmax + eps
+constexpr float kFocalEpsT = 1e-6f;     // kornia.utils.one_hot: scatter(1.0) + eps
+
+// One pixel of the focal criterion: e[c] = exp(l_c - max), se = sum e.  Returns the loss and writes the
+// gradient w.r.t. the logits (unscaled) into g[].
+template <int NC>
+__device__ __forceinline__ float focal_pixel(const float (&e)[NC], float se, int cls, float alpha, float gamma, float (&g)[NC]) {
+    const float inv = __fdividef(1.0f, se);
+    float loss = 0.f, dot = 0.f, pr[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        pr[c] = e[c] * inv;
+        const float pt = pr[c] + kFocalEpsP, om = 1.0f - pt;
+        const float lg = __log2f(pt) * 0.6931471805599453f;
+        const float t = (c == cls ? 1.0f : 0.0f) + kFocalEpsT;
+        float w, dw;                         // (1-p~)^gamma and gamma (1-p~)^(gamma-1)
+        if (gamma == 2.0f) { w = om * om; dw = 2.0f * om; }
+        else { w = __powf(fmaxf(om, 0.f), gamma); dw = gamma * __powf(fmaxf(om, 0.f), gamma - 1.0f); }
+        loss = fmaf(t, -alpha * w * lg, loss);
+        g[c] = t * alpha * (dw * lg - __fdividef(w, pt));
+        dot = fmaf(g[c], pr[c], dot);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) g[c] = pr[c] * (g[c] - dot);
+    return loss;
+}
 
 __device__ __forceinline__ float ex2a(float x) {
     float y;
@@ -44,8 +79,8 @@ __device__ __forceinline__ float ex2a(float x) {
     return y;
 }
 
-template <int NC>
-__global__ void __launch_bounds__(kCsThreads, 4) k_consist(const __grid_constant__ ConsistParams p) {
+template <int NC, int KIND>
+__global__ void __launch_bounds__(kCsThreads, KIND == 0 ? 4 : 3) k_consist(const __grid_constant__ ConsistParams p) {
     __shared__ float s_w[kCsThreads / 32];
     __shared__ int s_last;
     const long long stride = (long long)gridDim.x * kCsThreads;
@@ -79,12 +114,22 @@ __global__ void __launch_bounds__(kCsThreads, 4) k_consist(const __grid_constant
                 se += e[c];
                 if (c == cls) sel = lv[c];
             }
-            acc += fmaf(__log2f(se), 0.6931471805599453f, mx) - sel;
-            const float inv = __fdividef(p.gscale, se);
+            if (KIND == 0) {
+                acc += fmaf(__log2f(se), 0.6931471805599453f, mx) - sel;
+                const float inv = __fdividef(p.gscale, se);
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const float gv = fmaf(e[c], inv, c == cls ? -p.gscale : 0.f);
-                if (j == 0) g[c].x = gv; else if (j == 1) g[c].y = gv; else if (j == 2) g[c].z = gv; else g[c].w = gv;
+                for (int c = 0; c < NC; ++c) {
+                    const float gv = fmaf(e[c], inv, c == cls ? -p.gscale : 0.f);
+                    if (j == 0) g[c].x = gv; else if (j == 1) g[c].y = gv; else if (j == 2) g[c].z = gv; else g[c].w = gv;
+                }
+            } else {
+                float gp[NC];
+                acc += focal_pixel<NC>(e, se, cls, p.alpha, p.gamma, gp);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const float gv = gp[c] * p.gscale;
+                    if (j == 0) g[c].x = gv; else if (j == 1) g[c].y = gv; else if (j == 2) g[c].z = gv; else g[c].w = gv;
+                }
             }
         }
         if (p.dlogits) {
@@ -136,6 +181,21 @@ __global__ void __launch_bounds__(kCsThreads) k_consist_generic(const __grid_con
             se += ex2a(fmaf(v, k, mk));
             if (c == cls) sel = v;
         }
+        if (p.kind == 1) {                    // focal: pad the class vector to kCsMaxNc with zero probabilities
+            float e[kCsMaxNc], gp[kCsMaxNc];
+#pragma unroll
+            for (int c = 0; c < kCsMaxNc; ++c) e[c] = c < nc ? ex2a(fmaf(__ldg(lg + (long long)c * p.plane), k, mk)) : 0.f;
+            // classes >= nc do not exist in the reference: remove their eps-only terms again
+            float loss = focal_pixel<kCsMaxNc>(e, se, cls, p.alpha, p.gamma, gp);
+            const float lpad = -p.alpha * __log2f(kFocalEpsP) * 0.6931471805599453f *
+                               (p.gamma == 2.0f ? (1.0f - kFocalEpsP) * (1.0f - kFocalEpsP) : __powf(1.0f - kFocalEpsP, p.gamma));
+            acc += loss - (float)(kCsMaxNc - nc) * kFocalEpsT * lpad;
+            if (p.dlogits) {
+                float* dg = p.dlogits + (b * nc) * p.plane + r;
+                for (int c = 0; c < nc; ++c) dg[(long long)c * p.plane] = gp[c] * p.gscale;
+            }
+            continue;
+        }
         acc += fmaf(__log2f(se), 0.6931471805599453f, mx) - sel;
         if (p.dlogits) {
             const float inv = __fdividef(p.gscale, se);
@@ -173,9 +233,9 @@ extern "C" {
 
 int64_t sfh_consist_workspace_bytes(void) { return 256 + (int64_t)kCsMaxCtas * 4; }
 
-int sfh_consist_loss_fwd_bwd(const float* warp_mask, const float* logits, int B, int nc, int H, int W,
-                             float lambda, float* loss_out, float* dlogits,
-                             void* workspace, int64_t workspace_bytes, void* stream) {
+static int consist_launch(const float* warp_mask, const float* logits, int B, int nc, int H, int W, int kind,
+                          float alpha, float gamma, float lambda, float* loss_out, float* dlogits,
+                          void* workspace, int64_t workspace_bytes, void* stream) {
     if (!warp_mask || !logits || !loss_out || B <= 0 || H <= 0 || W <= 0) return SFH_E_BADARG;
     if (nc < 1 || nc > kCsMaxNc) return SFH_E_BADARG;
     if (!workspace || workspace_bytes < sfh_consist_workspace_bytes()) return SFH_E_WS;
@@ -187,15 +247,32 @@ int sfh_consist_loss_fwd_bwd(const float* warp_mask, const float* logits, int B,
     p.total_px = (long long)B * p.plane;
     p.quads = p.total_px / 4;
     p.ncf = (float)nc; p.lambda = lambda; p.nc = nc;
+    p.kind = kind; p.alpha = alpha; p.gamma = gamma;
     p.gscale = (float)((double)lambda / (double)p.total_px);
     const bool vec = (p.plane % 4 == 0) && (((uintptr_t)warp_mask | (uintptr_t)logits | (uintptr_t)dlogits) & 15u) == 0;
     cudaStream_t st = (cudaStream_t)stream;
     const long long work = (vec && nc == 4) ? p.quads : p.total_px;
     long long ctas = (work + kCsThreads - 1) / kCsThreads;
     if (ctas > kCsMaxCtas) ctas = kCsMaxCtas;
-    if (vec && nc == 4) k_consist<4><<<(int)ctas, kCsThreads, 0, st>>>(p);
-    else                k_consist_generic<<<(int)ctas, kCsThreads, 0, st>>>(p);
+    if (vec && nc == 4 && kind == 0) k_consist<4, 0><<<(int)ctas, kCsThreads, 0, st>>>(p);
+    else if (vec && nc == 4)         k_consist<4, 1><<<(int)ctas, kCsThreads, 0, st>>>(p);
+    else                             k_consist_generic<<<(int)ctas, kCsThreads, 0, st>>>(p);
     return (int)cudaGetLastError();
+}
+
+int sfh_consist_loss_fwd_bwd(const float* warp_mask, const float* logits, int B, int nc, int H, int W,
+                             float lambda, float* loss_out, float* dlogits,
+                             void* workspace, int64_t workspace_bytes, void* stream) {
+    return consist_launch(warp_mask, logits, B, nc, H, W, 0, 1.0f, 2.0f, lambda, loss_out, dlogits,
+                          workspace, workspace_bytes, stream);
+}
+
+int sfh_consist_focal_fwd_bwd(const float* warp_mask, const float* logits, int B, int nc, int H, int W,
+                              float alpha, float gamma, float lambda, float* loss_out, float* dlogits,
+                              void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!(gamma >= 0.f)) return SFH_E_BADARG;
+    return consist_launch(warp_mask, logits, B, nc, H, W, 1, alpha, gamma, lambda, loss_out, dlogits,
+                          workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -36,8 +36,8 @@ struct FusedParams {
                          // 0: the sample's last-dispatched CTA reduces them inside this launch (tagged slots, no fence)
     int fin_slots;       // partial slots per sample read by k_train_finalize
     int short_last;      // H % (8R) != 0: the short bottom tiles of all samples are dispatched last (shorter tail)
-    int lean, compact;   // development switches (SFH_NO_LEAN / SFH_NO_COMPACT clear them): guard-free geometry in proven-safe
-                         // patches; compacted edge-pixel pass of the bilinear epilogues
+    int lean, compact, fast_free;   // development switches (SFH_NO_LEAN / SFH_COMPACT / SFH_NO_FAST): guard-free geometry in
+                         // proven-safe patches; compacted edge-pixel pass of the bilinear epilogues; dedicated edge-free loop
     // kEpiStore / kEpiBwd
     float* out_f;        // [B,C,H,W]
     const float* grad_out;
@@ -396,6 +396,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     unsigned short (*s_list)[kListCap] = reinterpret_cast<unsigned short (*)[kListCap]>(s_scratch);
     __shared__ unsigned short s_items[kMaxR * kWarps];   // patch id | (class+1) << 8 | lean << 15, edge patches first
     __shared__ int s_ecnt[kWarps];
+    __shared__ int s_nedge;
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ unsigned s_epoch;
 
@@ -510,6 +511,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             if (w < warp) before += c;
         }
         const int pos = is_edge ? before : total + ((int)threadIdx.x - before);
+        if (threadIdx.x == 0) s_nedge = total;
         s_items[pos] = (unsigned short)(threadIdx.x | ((cls + 1) << 8) | (lean ? 0x8000 : 0));
     }
     __syncthreads();
@@ -577,8 +579,56 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         __syncwarp();
     };
 
+    // ---- edge-free patches of full tiles: a loop of their own, stripped to the stream --------------------------
+    // (the list holds the edge patches first; a warp's entries w, w+8, ... past `s_nedge` are edge-free).  Per patch:
+    // one item word, two 128-bit smem loads of the staged gt (loss), the constant compare, one 128-bit store.
+    const bool fast = FT && classify && p.fast_free &&
+                      (EPI == kEpiStore || (EPI == kEpiLoss && tma) ||
+                       (EPI == kEpiPredict && (!p.score || p.ratio == 0 || (p.ratio == 2 && tma))));
+    const int n_generic = fast ? s_nedge : nitems;
+    if (fast) {
+        const size_t lane_out = base_b + (size_t)(band0 + ly) * W + (tx * kTileW + lx * 4);
+        const int lane_smem = ly * kTileW + lx * 4;                       // element offset inside the staged tile
+        const float inv_nc = p.inv_nc;
+        const bool pow2 = p.nc_pow2 != 0;
 #pragma unroll 1
-    for (int it = warp; it < nitems; it += kWarps) {
+        for (int it = warp + ((n_generic - warp + kWarps - 1) & ~(kWarps - 1)); it < nitems; it += kWarps) {
+            const unsigned item = s_items[it];
+            const int pr = (item & 0x7fu) >> 3, pk = item & 7u, pc = (int)((item >> 8) & 0x7fu) - 1;
+            const float cval = taps.class_value(pc);
+            const size_t o = lane_out + (unsigned)(pr * 8 * W + pk * kPatchW);
+            if (EPI == kEpiStore) __stcs((float4*)(p.out_f + o), make_float4(cval, cval, cval, cval));
+            if (EPI == kEpiLoss) {
+                const int so = lane_smem + pr * 8 * kTileW + pk * kPatchW;
+                float gf[4];
+                if (p.gt8) {
+                    const uchar4 g8 = *reinterpret_cast<const uchar4*>(s_dyn + so);
+                    gf[0] = (float)g8.x; gf[1] = (float)g8.y; gf[2] = (float)g8.z; gf[3] = (float)g8.w;
+                } else {
+                    const longlong2* sp2 = reinterpret_cast<const longlong2*>(s_gt + so);
+                    const longlong2 lo = sp2[0], hi = sp2[1];
+                    gf[0] = (float)(int)lo.x; gf[1] = (float)(int)lo.y; gf[2] = (float)(int)hi.x; gf[3] = (float)(int)hi.y;
+                }
+                if (p.out_f) __stcs((float4*)(p.out_f + o), make_float4(cval, cval, cval, cval));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d = cval - (pow2 ? __fmul_rn(gf[j], inv_nc) : __fdiv_rn(gf[j], ncf));
+                    loss_sum += (kMse || fabsf(d) < 1.0f) ? d * d : 2.0f * fabsf(d) - 1.0f;
+                }
+            }
+            if (EPI == kEpiPredict) {
+                const int ci = __float2int_rz(__fmul_rn(cval, ncf));
+                if (p.out_u8) __stcs((uchar4*)(p.out_u8 + o), make_uchar4(ci, ci, ci, ci));
+                else __stcs((int4*)(p.out_i + o), make_int4(ci, ci, ci, ci));
+                if (p.score && p.ratio == 2)
+                    score_sum += ce_patch_lane<true>(reinterpret_cast<const float*>(s_dyn), R * 4 * (kTileW / 2), pr, pk, lane,
+                                                     ci, band0 + pr * 8, tx * kTileW + pk * kPatchW, H, W);
+            }
+        }
+    }
+
+#pragma unroll 1
+    for (int it = warp; it < n_generic; it += kWarps) {
         const unsigned item = s_items[it];
         const int pr = (item & 0xffu) >> 3, pk = item & 7u, pc = (int)((item >> 8) & 0x7fu) - 1;
         const bool lean_patch = (item & 0x8000u) != 0u;
@@ -1235,9 +1285,11 @@ static void fill_common(FusedParams& p, const float* theta, const sfh_template* 
         while (R > 1 && (int64_t)tiles_x * ((H + kWarps * R - 1) / (kWarps * R)) * B < 4 * 3 * 148) R >>= 1;
     p.rows_per_warp = R;
     p.ntiles = tiles_x * ((H + kWarps * R - 1) / (kWarps * R));
-    static const bool no_lean = getenv("SFH_NO_LEAN") != nullptr, no_compact = getenv("SFH_NO_COMPACT") != nullptr;
+    static const bool no_lean = getenv("SFH_NO_LEAN") != nullptr, compact = getenv("SFH_COMPACT") != nullptr,
+                      no_fast = getenv("SFH_NO_FAST") != nullptr;
     p.lean = no_lean ? 0 : 1;
-    p.compact = no_compact ? 0 : 1;
+    p.compact = compact ? 1 : 0;       // measured slower than the in-patch path on B200: opt-in
+    p.fast_free = no_fast ? 0 : 1;
 }
 
 static inline bool aligned16(const void* q) { return ((uintptr_t)q & 15u) == 0; }

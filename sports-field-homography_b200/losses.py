@@ -116,10 +116,15 @@ def _check_consist_args(logits, warp_mask, num_classes):
         raise ValueError("num_classes must be in 1..8")
 
 
-def consistency_step(logits, warp_mask, num_classes, consist_lambda=1.0, need_grad=True, out=None):
+def consistency_step(logits, warp_mask, num_classes, consist_lambda=1.0, need_grad=True, out=None,
+                     criterion="CE", alpha=1.0, gamma=2.0):
     """``consist_lambda * CrossEntropyLoss()(logits, (warp_mask * num_classes).long())`` and its
     gradient w.r.t. ``logits`` in ONE streaming launch (no log_softmax tensor, no int64 mask).
+    ``criterion='focal'`` selects train.py:133-134's ``kornia.losses.FocalLoss(alpha, gamma, 'mean')`` instead
+    (kornia 0.5.x eps conventions, see include/sfh_b200.h).
     Returns ``{"loss": scalar tensor, "dlogits": [B,nc,H,W] or None}``; ``out`` reuses buffers."""
+    if criterion not in ("CE", "focal"):
+        raise NotImplementedError(criterion)
     _check_consist_args(logits, warp_mask, num_classes)
     B, nc, H, W = logits.shape
     logits = logits.contiguous()
@@ -135,29 +140,38 @@ def consistency_step(logits, warp_mask, num_classes, consist_lambda=1.0, need_gr
             dl = out["dlogits"] = torch.empty_like(logits)
     ws = _consist_ws(logits.device)
     with torch.cuda.device(logits.device):
-        rc = _lib.lib().sfh_consist_loss_fwd_bwd(warp_mask.data_ptr(), logits.data_ptr(), B, nc, H, W,
-                                                 float(consist_lambda), loss.data_ptr(),
-                                                 dl.data_ptr() if dl is not None else None,
-                                                 ws.data_ptr(), ws.numel(), _stream())
-    _lib.check(rc, "sfh_consist_loss_fwd_bwd")
+        if criterion == "CE":
+            rc = _lib.lib().sfh_consist_loss_fwd_bwd(warp_mask.data_ptr(), logits.data_ptr(), B, nc, H, W,
+                                                     float(consist_lambda), loss.data_ptr(),
+                                                     dl.data_ptr() if dl is not None else None,
+                                                     ws.data_ptr(), ws.numel(), _stream())
+        else:
+            rc = _lib.lib().sfh_consist_focal_fwd_bwd(warp_mask.data_ptr(), logits.data_ptr(), B, nc, H, W,
+                                                      float(alpha), float(gamma), float(consist_lambda), loss.data_ptr(),
+                                                      dl.data_ptr() if dl is not None else None,
+                                                      ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "sfh_consist_loss_fwd_bwd" if criterion == "CE" else "sfh_consist_focal_fwd_bwd")
     return {"loss": loss, "dlogits": dl}
 
 
 class _ConsistFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, warp_mask, num_classes, consist_lambda):
-        r = consistency_step(logits, warp_mask, num_classes, consist_lambda, need_grad=logits.requires_grad)
+    def forward(ctx, logits, warp_mask, num_classes, consist_lambda, criterion, alpha, gamma):
+        r = consistency_step(logits, warp_mask, num_classes, consist_lambda, need_grad=logits.requires_grad,
+                             criterion=criterion, alpha=alpha, gamma=gamma)
         ctx.dl = r["dlogits"]
         return r["loss"].clone()
 
     @staticmethod
     def backward(ctx, g):
         if ctx.dl is None:                      # logits did not require grad at forward time
-            return None, None, None, None
-        return ctx.dl * g.to(torch.float32), None, None, None       # out of place: backward may run twice
+            return (None,) * 7
+        return (ctx.dl * g.to(torch.float32),) + (None,) * 6        # out of place: backward may run twice
 
 
-def consistency_loss(logits, warp_mask, num_classes, consist_lambda=1.0):
-    """Differentiable (w.r.t. ``logits``) form of train.py:221-222; no gradient reaches ``warp_mask``
-    — the reference's ``.to(dtype=torch.long)`` cuts it the same way."""
-    return _ConsistFn.apply(logits, warp_mask.detach(), int(num_classes), float(consist_lambda))
+def consistency_loss(logits, warp_mask, num_classes, consist_lambda=1.0, criterion="CE", alpha=1.0, gamma=2.0):
+    """Differentiable (w.r.t. ``logits``) form of train.py:221-222 for both of the reference's consistency
+    criteria (train.py:131-134: 'CE' -> nn.CrossEntropyLoss(), 'focal' -> kornia FocalLoss(alpha=1, gamma=2,
+    'mean')); no gradient reaches ``warp_mask`` — the reference's ``.to(dtype=torch.long)`` cuts it the same way."""
+    return _ConsistFn.apply(logits, warp_mask.detach(), int(num_classes), float(consist_lambda),
+                            criterion, float(alpha), float(gamma))

@@ -289,3 +289,20 @@ def test_postprocess_restatement_matches_cv2_and_golden_tables():
     for (ow, oh) in [(128, 72), (100, 50), (64, 36), (31, 17), (200, 111)]:
         for arr in (m[0], rgb[0]):
             assert np.array_equal(pr.resize_nearest(arr, (ow, oh)), cv2.resize(arr, (ow, oh), interpolation=cv2.INTER_NEAREST))
+
+
+def test_restated_focal_loss_closed_form():
+    """kornia 0.5.x focal_loss conventions pinned on a hand-computed case: two equal logits -> p = 0.5,
+    softmax + 1e-8, one-hot target + 1e-6 on BOTH classes (kornia.utils.one_hot adds its eps everywhere)."""
+    import math
+    from oracle import kornia_restated as kr
+    lg = torch.zeros(1, 2, 1, 1, dtype=torch.float64)
+    t = torch.zeros(1, 1, 1, dtype=torch.long)
+    p = 0.5 + 1e-8
+    term = -(1 - p) ** 2 * math.log(p)
+    assert abs(float(kr.focal_loss(lg, t, 1.0, 2.0, "mean")) - ((1 + 1e-6) * term + 1e-6 * term)) < 1e-15
+    # gamma = 0, alpha = 1 degenerates to (eps-perturbed) cross entropy
+    lg = torch.randn(2, 4, 3, 5, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    t = torch.randint(0, 4, (2, 3, 5), generator=torch.Generator().manual_seed(1))
+    ce = torch.nn.functional.cross_entropy(lg, t)
+    assert abs(float(kr.focal_loss(lg, t, 1.0, 0.0, "mean")) - float(ce)) < 1e-4

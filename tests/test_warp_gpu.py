@@ -817,6 +817,81 @@ def test_predict_tail_bilinear_int_masks_match_oracle_in_production_mode():
 
 
 
+# ------------------------------------------------------------------ SURVEY §8 f-2 (focal) and f-4 (tooling)
+@pytest.mark.parametrize("W,H,B,nc,gamma", [(640, 360, 3, 4, 2.0), (200, 76, 2, 4, 1.5), (130, 50, 2, 3, 2.0), (64, 36, 2, 7, 2.0)])
+def test_focal_consistency_matches_restated_kornia(W, H, B, nc, gamma):
+    """train.py:133-134: kornia.losses.FocalLoss(alpha=1, gamma=2, 'mean') as the consistency criterion — loss and
+    dlogits against fp64 autograd of the restated kornia 0.5.x focal_loss (softmax + 1e-8, one_hot + 1e-6)."""
+    g = torch.Generator().manual_seed(W + nc)
+    logits = torch.randn(B, nc, H, W, generator=g) * 3.0
+    wm = torch.randint(0, nc, (B, 1, H, W), generator=g).float() / nc
+    lam, alpha = 0.7, 1.0
+    lg64 = logits.double().requires_grad_(True)
+    ref = kr.consistency_loss_focal(lg64, wm.double(), nc, lam, alpha, gamma)
+    ref.backward()
+    lgd = logits.to(DEV).requires_grad_(True)
+    got = sfh_b200.consistency_loss(lgd, wm.to(DEV), nc, lam, criterion="focal", alpha=alpha, gamma=gamma)
+    got.backward()
+    assert abs(float(got) - float(ref)) <= 2e-5 * abs(float(ref)), (float(got), float(ref))
+    gr = lg64.grad
+    assert float((lgd.grad.cpu().double() - gr).abs().max()) <= 2e-5 * float(gr.abs().max())
+    # evaluation form (no gradient buffer) gives the same loss
+    ev = sfh_b200.consistency_step(logits.to(DEV), wm.to(DEV), nc, lam, need_grad=False, criterion="focal", gamma=gamma)
+    assert ev["dlogits"] is None and float(ev["loss"]) == float(got)
+
+
+@pytest.mark.parametrize("grid_dtype", [torch.float32, torch.float64])
+def test_fp64_multichannel_nearest_warper_matches_restated_kornia(grid_dtype):
+    """utils/transform.py:7-20 Warper: fp64 [H,W,C] projection, nearest, kornia in double — bit-exact copies."""
+    rng = np.random.default_rng(5)
+    Hc, Wc, C, W, H = 90, 160, 3, 128, 72
+    proj = rng.normal(size=(Hc, Wc, C))
+    for k in range(4):
+        theta = (np.eye(3) + rng.uniform(-0.25, 0.25, (3, 3))) * rng.uniform(1, 15)
+        got = sfh_b200.Warper((W, H), grid_dtype=grid_dtype).warp(theta, proj)
+        pt = torch.from_numpy(proj).permute(2, 0, 1).unsqueeze(0)
+        ref = kr.HomographyWarper(H, W, mode="nearest", grid_dtype=grid_dtype)(pt, torch.from_numpy(theta).unsqueeze(0))[0]
+        ref = ref.permute(1, 2, 0).numpy()
+        assert got.shape == (H, W, C) and got.dtype == np.float64
+        assert np.array_equal(got, ref), float((got != ref).mean())
+    # same on the device restatement (what utils/transform.py runs with cuda=True), batched form
+    th = torch.from_numpy(np.stack([np.eye(3) + rng.uniform(-0.2, 0.2, (3, 3)) for _ in range(5)])).to(DEV)
+    pj = torch.from_numpy(proj).permute(2, 0, 1).unsqueeze(0).to(DEV)
+    out = sfh_b200.Warper((W, H), grid_dtype=grid_dtype).warp_tensor(th, pj)
+    refd = kr.HomographyWarper(H, W, mode="nearest", grid_dtype=grid_dtype)(pj.expand(5, -1, -1, -1), th)
+    assert (out != refd).double().mean() <= 1e-5        # CUDA's `tensor / scalar` meshgrid differs by an ulp on a few columns
+
+
+def test_warp_perspective_nearest_matches_cv2():
+    """Dataset mask rendering (football_dataset.ipynb cell 11): cv2.warpPerspective(FIELD_MASK, rescale_theta(...),
+    FIELD_SIZE, flags=cv2.INTER_NEAREST) — uint8 BGR masks and the fp64 UV templates, against real cv2."""
+    import cv2
+    rng = np.random.default_rng(11)
+    tmpl, _ = sfh_b200.load_bundled("pitch_v3_nc4", (1280, 720), 4, 1)
+    cls = (tmpl[0, 0] * 4).round().to(torch.uint8).numpy()
+    colours = np.array([[0, 0, 0], [0, 255, 0], [255, 0, 0], [0, 0, 255]], np.uint8)       # preparation.py:219-221 (BGR)
+    field = colours[cls]                                                                      # [720,1280,3] uint8
+    uv = (np.mgrid[0:720, 0:1280][1] / 1280.0).astype(np.float64)[..., None]                 # U template, fp64 [H,W,1]
+    thetas = []
+    for k in range(6):
+        th = np.eye(3) + rng.uniform(-0.15, 0.15, (3, 3))
+        th[2, :2] *= 0.3
+        thetas.append(th)
+    Ms = sfh_b200.rescale_theta((1280, 720), (1280, 720), np.stack(thetas))
+    ref_scaled = np.matmul(np.matmul(np.diag([1280.0, 720.0, 1.0]), thetas[0]), np.diag([1 / 1280.0, 1 / 720.0, 1.0]))
+    assert np.allclose(Ms[0], ref_scaled, rtol=1e-15, atol=0)
+    got = sfh_b200.warp_perspective_nearest(torch.from_numpy(field).to(DEV), Ms, (1280, 720)).cpu().numpy()
+    gotuv = sfh_b200.warp_perspective_nearest(torch.from_numpy(uv).to(DEV), Ms, (640, 360)).cpu().numpy()
+    for k in range(6):
+        ref = cv2.warpPerspective(field, Ms[k], (1280, 720), flags=cv2.INTER_NEAREST)
+        assert np.array_equal(got[k], ref), float((got[k] != ref).mean())
+        refuv = cv2.warpPerspective(uv, Ms[k], (640, 360), flags=cv2.INTER_NEAREST)
+        assert np.array_equal(gotuv[k][..., 0], refuv)
+    one = sfh_b200.warp_perspective_nearest(torch.from_numpy(cls).to(DEV), Ms[2], (300, 200))   # single M, single channel
+    assert np.array_equal(one.cpu().numpy(), cv2.warpPerspective(cls, Ms[2], (300, 200), flags=cv2.INTER_NEAREST))
+
+
+
 def test_error_conventions_and_state_dict():
     tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 2)
     st = mk_stage(tmpl.to(DEV), poi.to(DEV), (640, 360), 4)
