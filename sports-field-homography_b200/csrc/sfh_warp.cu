@@ -36,8 +36,8 @@ struct FusedParams {
                          // 0: the sample's last-dispatched CTA reduces them inside this launch (tagged slots, no fence)
     int fin_slots;       // partial slots per sample read by k_train_finalize
     int short_last;      // H % (8R) != 0: the short bottom tiles of all samples are dispatched last (shorter tail)
-    int lean, compact, fast_free;   // development switches (SFH_NO_LEAN / SFH_COMPACT / SFH_NO_FAST): guard-free geometry in
-                         // proven-safe patches; compacted edge-pixel pass of the bilinear epilogues; dedicated edge-free loop
+    int lean, fast_free; // development switches (SFH_NO_LEAN / SFH_NO_FAST clear them): guard-free geometry in proven-safe
+                         // patches; dedicated loop for the edge-free patches of full tiles
     // kEpiStore / kEpiBwd
     float* out_f;        // [B,C,H,W]
     const float* grad_out;
@@ -161,15 +161,6 @@ struct GradAcc {
         yu = fmaf(gY, u, yu); y1 += gY;
         zu = fmaf(gZ, u, zu); z1 += gZ;
     }
-    // one isolated pixel (the compacted edge-pixel pass): straight into the nine sums
-    __device__ __forceinline__ void add_px(const Pix& p, float gix, float giy, float halfWc, float halfHc, float u, float v) {
-        const float gx = gix * halfWc, gy = giy * halfHc;
-        const float gX = gx * p.f.s, gY = gy * p.f.s;
-        const float gZ = p.f.zok ? -(gx * p.f.X + gy * p.f.Y) * p.f.s * p.f.s : 0.f;
-        a[0] = fmaf(gX, u, a[0]); a[1] = fmaf(gX, v, a[1]); a[2] += gX;
-        a[3] = fmaf(gY, u, a[3]); a[4] = fmaf(gY, v, a[4]); a[5] += gY;
-        a[6] = fmaf(gZ, u, a[6]); a[7] = fmaf(gZ, v, a[7]); a[8] += gZ;
-    }
     __device__ __forceinline__ void end_row(float v) {
         a[0] += xu; a[1] = fmaf(x1, v, a[1]); a[2] += x1;
         a[3] += yu; a[4] = fmaf(y1, v, a[4]); a[5] += y1;
@@ -256,6 +247,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE_%=:\n\t}"
         :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// One 128-bit shared-memory load that the compiler may not split: with 32 B per lane the four 32-bit words of a
+// quarter-warp's 128-bit access cover all banks once, whereas "load only the words that are used" (what nvcc makes
+// of a longlong2 whose high halves are dead) puts lanes i, i+4, i+8, ... on the same bank — an 8-way conflict.
+template <int OFF>
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(OFF));
+    return v;
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -316,7 +316,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 }
 
 constexpr int kMaxR = 16;        // bands (8 rows each) per CTA
-constexpr int kListCap = 32 + 128;   // a patch adds <= 128 pixels to a list that is drained below 32 after every patch
 constexpr int kPatchW = 16;      // a warp works on 16 x 8 pixel patches: lane = (ly 0..7, lx 0..3), 4 px per lane
 constexpr float kBoxMargin = 1.0f / 64.0f;   // slack (in texels) on the patch bounding box, >> fp32 rounding of ix
 
@@ -380,23 +379,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     extern __shared__ __align__(128) unsigned char s_dyn[];            // TMA destination (gt tile)
     __shared__ __align__(16) float s_tab[Taps<FMT>::kSmemFloats];
     __shared__ float s_red[kWarps][16];
-    // one scratch area, three tenants with disjoint lifetimes (3 CTAs/SM leave no smem to spare next to the 64 KiB
-    // gt tile): the corner grid (prologue, dead after the classification barrier), the per-warp edge-pixel lists
-    // (patch loop), the fp64 partial sums of the reducer CTA (after the end-of-loop barrier)
-    constexpr int kFinBytes = (int)sizeof(double) * kNPart * kFinGroup;                 // 2016
-    constexpr int kGridBytes = 3 * (kMaxR + 1) * (kWarps + 1) * (int)sizeof(float);     // 1836
-    constexpr int kListBytes = kWarps * kListCap * (int)sizeof(unsigned short);         // 2560
-    static_assert(kListBytes <= kFinBytes + kGridBytes, "lists must fit the shared scratch area");
-    __shared__ __align__(16) unsigned char s_scratch[kFinBytes + kGridBytes];
-    double (*s_fin)[kFinGroup] = reinterpret_cast<double (*)[kFinGroup]>(s_scratch);
-    float (*s_gx)[kWarps + 1] = reinterpret_cast<float (*)[kWarps + 1]>(s_scratch + kFinBytes);
-    float (*s_gy)[kWarps + 1] = s_gx + (kMaxR + 1);
-    float (*s_gz)[kWarps + 1] = s_gy + (kMaxR + 1);
-    // per warp: edge pixels (row << 7 | col inside the CTA tile) awaiting the compacted pass
-    unsigned short (*s_list)[kListCap] = reinterpret_cast<unsigned short (*)[kListCap]>(s_scratch);
+    __shared__ double s_fin[kNPart][kFinGroup];
+    __shared__ float s_gx[kMaxR + 1][kWarps + 1], s_gy[kMaxR + 1][kWarps + 1], s_gz[kMaxR + 1][kWarps + 1];
     __shared__ unsigned short s_items[kMaxR * kWarps];   // patch id | (class+1) << 8 | lean << 15, edge patches first
     __shared__ int s_ecnt[kWarps];
     __shared__ int s_nedge;
+    __shared__ signed char s_cls[kMaxR * kWarps];        // class of an edge-free patch, -1: touches an edge
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ unsigned s_epoch;
 
@@ -512,6 +500,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         }
         const int pos = is_edge ? before : total + ((int)threadIdx.x - before);
         if (threadIdx.x == 0) s_nedge = total;
+        s_cls[threadIdx.x] = (signed char)cls;
         s_items[pos] = (unsigned short)(threadIdx.x | ((cls + 1) << 8) | (lean ? 0x8000 : 0));
     }
     __syncthreads();
@@ -530,103 +519,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     if (tma) mbar_wait(&s_bar, 0);           // gt tile has landed (it streamed in behind the prologue)
     SFH_TL(3);
 
-    // ---- compacted edge-pixel pass (bilinear Store / Bwd / Loss epilogues on packed templates) -----------------
-    // In a patch that touches a class edge only the pixels whose OWN 2x2 footprint straddles the edge (3-4 % of
-    // all pixels) need weights, interpolation and the chain rule; every other pixel samples one class and is a
-    // constant with zero gradient, exactly like the pixels of an edge-free patch.  The patch pass therefore only
-    // computes each pixel's exact texel coordinates and looks at its packed entry; pixels with a mixed entry are
-    // appended to a per-warp list and processed 32 at a time — one pixel per lane, all lanes busy — by flush().
-    constexpr bool kCompact = (FMT != SFH_TMPL_F32) && (SMODE == SFH_MODE_BILINEAR) &&
-                              (EPI == kEpiStore || EPI == kEpiBwd || EPI == kEpiLoss);
-    int ncnt = 0;                            // entries in this warp's list (warp-uniform)
-    auto flush = [&](int n) {                // the top n (<= 32) entries of the list
-        __syncwarp();
-        if (lane < n) {
-            const unsigned e = s_list[warp][ncnt - n + lane];
-            const int r = (int)(e >> 7), c = (int)(e & 127u);
-            const int prow = band0 + r, pcol = tx * kTileW + c;                 // inside the image by construction
-            const float uu = p.xs ? __ldg(p.xs + pcol) : mesh_coord(pcol, W);
-            const float vv = p.ys ? __ldg(p.ys + prow) : mesh_coord(prow, H);
-            const Pix q = pixel_geom_lean<SFH_MODE_BILINEAR>(Hm, uu, vv, Wc_f, Hc_f);
-            const TapVals t = taps.fetch4(0, q.x0, q.y0);
-            const size_t pix = base_b + (unsigned)(prow * W + pcol);
-            float g = 0.f;
-            if (EPI == kEpiStore || EPI == kEpiLoss) {
-                const float o = bilerp(q, t);
-                if (EPI == kEpiStore || p.out_f) p.out_f[pix] = o;
-                if (EPI == kEpiLoss) {
-                    float gfv;
-                    if (p.gt8) gfv = (float)(tma ? s_dyn[r * kTileW + c] : p.gt8[pix]);
-                    else gfv = (float)(int)(tma ? s_gt[r * kTileW + c] : p.gt[pix]);
-                    const float tg = p.nc_pow2 ? __fmul_rn(gfv, p.inv_nc) : __fdiv_rn(gfv, ncf);
-                    const float d = o - tg;
-                    float l;
-                    if (kMse || fabsf(d) < 1.0f) { l = d * d; g = d; }
-                    else { l = 2.0f * fabsf(d) - 1.0f; g = d > 0.f ? 1.0f : -1.0f; }
-                    loss_sum += l;
-                    g *= gscale;
-                }
-            } else {
-                g = __ldcs(p.grad_out + pix);
-            }
-            if (EPI != kEpiStore) {
-                const float gix = ((t.b - t.a) * q.sy + (t.d - t.c) * q.ny) * g;
-                const float giy = ((t.c - t.a) * q.ex + (t.d - t.b) * q.wx) * g;
-                acc.add_px(q, gix, giy, halfWc, halfHc, uu, vv);
-            }
-        }
-        ncnt -= n;
-        __syncwarp();
-    };
-
-    // ---- edge-free patches of full tiles: a loop of their own, stripped to the stream --------------------------
-    // (the list holds the edge patches first; a warp's entries w, w+8, ... past `s_nedge` are edge-free).  Per patch:
-    // one item word, two 128-bit smem loads of the staged gt (loss), the constant compare, one 128-bit store.
+    // full tiles of packed templates: the list's leading `s_nedge` entries (the edge patches) go through the patch
+    // loop, the edge-free rest is streamed band by band further down
     const bool fast = FT && classify && p.fast_free &&
-                      (EPI == kEpiStore || (EPI == kEpiLoss && tma) ||
+                      (EPI == kEpiStore || EPI == kEpiLoss ||
                        (EPI == kEpiPredict && (!p.score || p.ratio == 0 || (p.ratio == 2 && tma))));
     const int n_generic = fast ? s_nedge : nitems;
-    if (fast) {
-        const size_t lane_out = base_b + (size_t)(band0 + ly) * W + (tx * kTileW + lx * 4);
-        const int lane_smem = ly * kTileW + lx * 4;                       // element offset inside the staged tile
-        const float inv_nc = p.inv_nc;
-        const bool pow2 = p.nc_pow2 != 0;
-#pragma unroll 1
-        for (int it = warp + ((n_generic - warp + kWarps - 1) & ~(kWarps - 1)); it < nitems; it += kWarps) {
-            const unsigned item = s_items[it];
-            const int pr = (item & 0x7fu) >> 3, pk = item & 7u, pc = (int)((item >> 8) & 0x7fu) - 1;
-            const float cval = taps.class_value(pc);
-            const size_t o = lane_out + (unsigned)(pr * 8 * W + pk * kPatchW);
-            if (EPI == kEpiStore) __stcs((float4*)(p.out_f + o), make_float4(cval, cval, cval, cval));
-            if (EPI == kEpiLoss) {
-                const int so = lane_smem + pr * 8 * kTileW + pk * kPatchW;
-                float gf[4];
-                if (p.gt8) {
-                    const uchar4 g8 = *reinterpret_cast<const uchar4*>(s_dyn + so);
-                    gf[0] = (float)g8.x; gf[1] = (float)g8.y; gf[2] = (float)g8.z; gf[3] = (float)g8.w;
-                } else {
-                    const longlong2* sp2 = reinterpret_cast<const longlong2*>(s_gt + so);
-                    const longlong2 lo = sp2[0], hi = sp2[1];
-                    gf[0] = (float)(int)lo.x; gf[1] = (float)(int)lo.y; gf[2] = (float)(int)hi.x; gf[3] = (float)(int)hi.y;
-                }
-                if (p.out_f) __stcs((float4*)(p.out_f + o), make_float4(cval, cval, cval, cval));
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float d = cval - (pow2 ? __fmul_rn(gf[j], inv_nc) : __fdiv_rn(gf[j], ncf));
-                    loss_sum += (kMse || fabsf(d) < 1.0f) ? d * d : 2.0f * fabsf(d) - 1.0f;
-                }
-            }
-            if (EPI == kEpiPredict) {
-                const int ci = __float2int_rz(__fmul_rn(cval, ncf));
-                if (p.out_u8) __stcs((uchar4*)(p.out_u8 + o), make_uchar4(ci, ci, ci, ci));
-                else __stcs((int4*)(p.out_i + o), make_int4(ci, ci, ci, ci));
-                if (p.score && p.ratio == 2)
-                    score_sum += ce_patch_lane<true>(reinterpret_cast<const float*>(s_dyn), R * 4 * (kTileW / 2), pr, pk, lane,
-                                                     ci, band0 + pr * 8, tx * kTileW + pk * kPatchW, H, W);
-            }
-        }
-    }
-
 #pragma unroll 1
     for (int it = warp; it < n_generic; it += kWarps) {
         const unsigned item = s_items[it];
@@ -723,54 +621,6 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                 }
             }
             continue;                        // kEpiBwd: zero gradient, grad_out is not even read
-        }
-
-        if (kCompact && lean_patch && p.compact) {
-            // ============ edge patch, compacted: constants here, mixed-footprint pixels to the list ============
-            const float v = p.ys ? __ldg(p.ys + rowc) : mesh_coord(rowc, H);
-            unsigned ent[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {    // exact texel coordinates (no weights), four entry loads in flight
-                const int cx = FT ? col + j : min(col + j, W - 1);
-                const float uj = p.xs ? __ldg(p.xs + cx) : mesh_coord(cx, W);
-                const Pix q = pixel_geom_lean<SFH_MODE_BILINEAR>(Hm, uj, v, Wc_f, Hc_f);
-                ent[j] = taps.quad(q.x0, q.y0);
-            }
-            float o[4];
-            unsigned em = 0u;                // pixels whose footprint mixes classes
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const TapVals t = taps.decode(ent[j]);
-                o[j] = t.a;                  // uniform footprint: the class value (a == b == c == d)
-                if (!t.uni && SFH_PIX_OK(j)) em |= 1u << j;
-            }
-            if (EPI == kEpiStore || (EPI == kEpiLoss && p.out_f)) {
-                // mixed pixels are rewritten by flush(); __syncwarp orders the two stores
-                if (vec) __stcs((float4*)(p.out_f + rowbase), make_float4(o[0], o[1], o[2], o[3]));
-                else
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if (SFH_PIX_OK(j)) p.out_f[rowbase + j] = o[j];
-            }
-            if (EPI == kEpiLoss) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float d = o[j] - tgt[j];
-                    float l = (kMse || fabsf(d) < 1.0f) ? d * d : 2.0f * fabsf(d) - 1.0f;
-                    if (!SFH_PIX_OK(j) || ((em >> j) & 1u)) l = 0.f;
-                    loss_sum += l;
-                }
-            }
-            const unsigned below = (1u << lane) - 1u;
-            const unsigned id0 = (unsigned)((pr * 8 + ly) << 7) | (unsigned)(pk * kPatchW + lx * 4);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool m = (em >> j) & 1u;
-                const unsigned bl = __ballot_sync(0xffffffffu, m);
-                if (m) s_list[warp][ncnt + __popc(bl & below)] = (unsigned short)(id0 + j);
-                ncnt += __popc(bl);
-            }
-            while (ncnt >= 32) flush(32);
-            continue;
         }
 
         // ======================= per-pixel path (patch touches a class edge) ====================
@@ -947,7 +797,116 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         }
     }
 #undef SFH_PIX_OK
-    if (kCompact && ncnt > 0) flush(ncnt);   // the remainder (< 32 pixels)
+    // ---- edge-free patches of full tiles, streamed band by band -------------------------------------------
+    // A band is one row of 8 patches (8 x 128 px).  A warp walks its bands row by row with lane i on pixels
+    // 4i..4i+3 of the row — 32 consecutive bytes of the staged int64 gt per lane, so the two 128-bit smem loads of
+    // a row are bank-conflict free (a patch-shaped access hits rows 1 KiB apart: same banks) and the global store is
+    // one contiguous 512 B line per row.  A lane's patch is column block i/4; lanes whose patch touches a class edge
+    // are predicated off (their patch went through the loop above).  Per patch this costs ~20 instructions instead
+    // of ~70: the per-patch bookkeeping is paid once per band.  Placed after the edge-patch loop, where the
+    // homography and the chain rule's row sums are dead, so it runs with few live registers.
+    if (fast) {
+        const int nbands = nitems >> 3;
+        const float inv_nc = p.inv_nc;
+        const bool pow2 = p.nc_pow2 != 0;
+        const bool hot = EPI == kEpiLoss && tma && !p.gt8 && pow2 && p.out_f != nullptr;
+#pragma unroll 1
+        for (int r = warp; r < nbands; r += kWarps) {
+            const int pc = s_cls[r * kWarps + (lane >> 2)];
+            const bool act = pc >= 0;
+            const float cval = taps.class_value(act ? pc : 0);
+            const float4 c4 = make_float4(cval, cval, cval, cval);
+            size_t o = base_b + (size_t)(band0 + r * 8) * W + (tx * kTileW + lane * 4);
+            if (EPI == kEpiStore) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k, o += W)
+                    if (act) __stcs((float4*)(p.out_f + o), c4);
+            }
+            if (EPI == kEpiLoss) {
+                int so = (r * 8) * kTileW + lane * 4;                    // element offset inside the staged tile
+                if (hot) {
+                    // the reference's own surface (int64 gt staged by TMA, nc a power of two, warp_mask wanted):
+                    // 2 LDS.128 + 4 I2F + 4 FFMA + 4 FFMA + 1 STG.128 per row.  fma(g, -1/nc, cval) == cval - g/nc
+                    // bit for bit here: g/nc is exact for a power-of-two nc.
+                    // Loads and stores use different lane->pixel maps.  A 128-bit smem load is conflict-free only if
+                    // the 8 lanes of a quarter-warp cover 128 contiguous bytes, so lane i loads gt pixels {2i, 2i+1}
+                    // and {64+2i, 64+2i+1} (patches i/8 and 4+i/8); the store stays one 128-bit line-friendly write of
+                    // pixels 4i..4i+3 (patch i/4).  The loss does not care which lane adds which pixel.
+                    const int pa = s_cls[r * kWarps + (lane >> 3)], pb = s_cls[r * kWarps + 4 + (lane >> 3)];
+                    const float ca = taps.class_value(pa >= 0 ? pa : 0), cb = taps.class_value(pb >= 0 ? pb : 0);
+                    const uint32_t sa = smem_u32(s_gt + (r * 8) * kTileW + lane * 2);
+                    float* op = p.out_f + o;
+                    const float ninv = -inv_nc;
+                    float la = 0.f, lb = 0.f;
+#define SFH_HOT_ROW(k) {                                                                                           \
+                        const uint4 lo = lds128<(k) * kTileW * 8>(sa), hi = lds128<(k) * kTileW * 8 + 512>(sa);               \
+                        if (act) __stcs((float4*)(op + (size_t)(k) * W), c4);                                                 \
+                        const float d0 = fmaf((float)(int)lo.x, ninv, ca), d1 = fmaf((float)(int)lo.z, ninv, ca);             \
+                        const float d2 = fmaf((float)(int)hi.x, ninv, cb), d3 = fmaf((float)(int)hi.z, ninv, cb);             \
+                        if (kMse) {                                                                                           \
+                            la = fmaf(d0, d0, la); la = fmaf(d1, d1, la); lb = fmaf(d2, d2, lb); lb = fmaf(d3, d3, lb);       \
+                        } else {                                                                                              \
+                            la += fabsf(d0) < 1.0f ? d0 * d0 : 2.0f * fabsf(d0) - 1.0f;                                       \
+                            la += fabsf(d1) < 1.0f ? d1 * d1 : 2.0f * fabsf(d1) - 1.0f;                                       \
+                            lb += fabsf(d2) < 1.0f ? d2 * d2 : 2.0f * fabsf(d2) - 1.0f;                                       \
+                            lb += fabsf(d3) < 1.0f ? d3 * d3 : 2.0f * fabsf(d3) - 1.0f;                                       \
+                        }                                                                                                     \
+                    }
+                    SFH_HOT_ROW(0) SFH_HOT_ROW(1) SFH_HOT_ROW(2) SFH_HOT_ROW(3)
+                    SFH_HOT_ROW(4) SFH_HOT_ROW(5) SFH_HOT_ROW(6) SFH_HOT_ROW(7)
+#undef SFH_HOT_ROW
+                    loss_sum += (pa >= 0 ? la : 0.f) + (pb >= 0 ? lb : 0.f);              // edge patches: handled above
+                    continue;
+                }
+#pragma unroll 2
+                for (int k = 0; k < 8; ++k, o += W, so += kTileW) {
+                    if (!act) continue;
+                    float gf[4];
+                    if (p.gt8) {
+                        const uchar4 g8 = tma ? *reinterpret_cast<const uchar4*>(s_dyn + so)
+                                              : __ldcs(reinterpret_cast<const uchar4*>(p.gt8 + o));
+                        gf[0] = (float)g8.x; gf[1] = (float)g8.y; gf[2] = (float)g8.z; gf[3] = (float)g8.w;
+                    } else {
+                        longlong2 lo, hi;
+                        if (tma) {
+                            const longlong2* sp2 = reinterpret_cast<const longlong2*>(s_gt + so);
+                            lo = sp2[0]; hi = sp2[1];
+                        } else {
+                            lo = __ldcs((const longlong2*)(p.gt + o)); hi = __ldcs((const longlong2*)(p.gt + o) + 1);
+                        }
+                        gf[0] = (float)(int)lo.x; gf[1] = (float)(int)lo.y; gf[2] = (float)(int)hi.x; gf[3] = (float)(int)hi.y;
+                    }
+                    if (p.out_f) __stcs((float4*)(p.out_f + o), c4);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float d = cval - (pow2 ? __fmul_rn(gf[j], inv_nc) : __fdiv_rn(gf[j], ncf));
+                        loss_sum += (kMse || fabsf(d) < 1.0f) ? d * d : 2.0f * fabsf(d) - 1.0f;
+                    }
+                }
+            }
+            if (EPI == kEpiPredict) {
+                const int ci = __float2int_rz(__fmul_rn(cval, ncf));
+#pragma unroll
+                for (int k = 0; k < 8; ++k, o += W) {
+                    if (!act) continue;
+                    if (p.out_u8) __stcs((uchar4*)(p.out_u8 + o), make_uchar4(ci, ci, ci, ci));
+                    else __stcs((int4*)(p.out_i + o), make_int4(ci, ci, ci, ci));
+                }
+                if (p.score && p.ratio == 2 && act) {
+                    // the band's 4 x 64 staged logits pixels: lane i owns pixels 2i, 2i+1 of each row; both sit
+                    // under this lane's patch (F.interpolate(nearest) picks source pixel (2i, 2j))
+                    const float* sl = reinterpret_cast<const float*>(s_dyn) + (r * 4) * (kTileW / 2) + lane * 2;
+                    const int cst = R * 4 * (kTileW / 2);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k, sl += kTileW / 2) {
+                        const float2 l0 = *reinterpret_cast<const float2*>(sl), l1 = *reinterpret_cast<const float2*>(sl + cst);
+                        const float2 l2 = *reinterpret_cast<const float2*>(sl + 2 * cst), l3 = *reinterpret_cast<const float2*>(sl + 3 * cst);
+                        score_sum += ce4(l0.x, l1.x, l2.x, l3.x, ci) + ce4(l0.y, l1.y, l2.y, l3.y, ci);
+                    }
+                }
+            }
+        }
+    }
 
     if (EPI == kEpiStore) return;
     if (EPI == kEpiPredict && !(p.score && p.ratio != 0)) return;
@@ -1285,10 +1244,8 @@ static void fill_common(FusedParams& p, const float* theta, const sfh_template* 
         while (R > 1 && (int64_t)tiles_x * ((H + kWarps * R - 1) / (kWarps * R)) * B < 4 * 3 * 148) R >>= 1;
     p.rows_per_warp = R;
     p.ntiles = tiles_x * ((H + kWarps * R - 1) / (kWarps * R));
-    static const bool no_lean = getenv("SFH_NO_LEAN") != nullptr, compact = getenv("SFH_COMPACT") != nullptr,
-                      no_fast = getenv("SFH_NO_FAST") != nullptr;
+    static const bool no_lean = getenv("SFH_NO_LEAN") != nullptr, no_fast = getenv("SFH_NO_FAST") != nullptr;
     p.lean = no_lean ? 0 : 1;
-    p.compact = compact ? 1 : 0;       // measured slower than the in-patch path on B200: opt-in
     p.fast_free = no_fast ? 0 : 1;
 }
 
