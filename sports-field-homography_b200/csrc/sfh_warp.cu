@@ -954,8 +954,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     if (p.split_finalize) return;                        // reduced by k_train_finalize / k_comp_finalize (next launch)
     if (tileE != p.ntiles - 1) return;
     {
+        // components this epilogue produces: loss + 9 dtheta terms / the 9 dtheta terms / the score
+        constexpr int kLo = (EPI == kEpiLoss) ? 0 : (EPI == kEpiBwd) ? 1 : 10;
+        constexpr int kHi = (EPI == kEpiPredict) ? 11 : 10;
         const int k = threadIdx.x / kFinGroup, jj = threadIdx.x % kFinGroup;
-        if (k < kNPart) {
+        if (k < kNPart) s_fin[k][jj] = 0.0;
+        if (k >= kLo && k < kHi) {
             double s = 0.0;
             const unsigned long long* base = reinterpret_cast<const unsigned long long*>(p.partials) + (size_t)bE * p.ntiles * kNPart + k;
             for (int t0 = jj; t0 < p.ntiles; t0 += 4 * kFinGroup) {
