@@ -594,6 +594,27 @@ def run_c5(dev, world, rank, use_graph, dist_ring):
     return out
 
 
+def pin_to_gpu_numa_node(index):
+    """Restrict this rank to the CPU cores NVML reports as local to its GPU, so that the pinned host buffers of the
+    e2e leg are first-touched on the GPU's own NUMA node (8 ranks pulling 50 GB/s each through one socket's memory
+    controllers is what flattened the round-1 e2e scaling).  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = sorted(local & allowed)
+        if use and len(use) < len(allowed):
+            os.sched_setaffinity(0, use)
+            return f"rank pinned to {len(use)} GPU-local cores ({use[0]}-{use[-1]})"
+        return f"GPU-local cores = all {len(allowed)} visible cores (single NUMA node visible)"
+    except Exception as e:
+        return f"not pinned ({e!r})"
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -610,6 +631,7 @@ def main_ours(args):
         raise SystemExit(subprocess.call(cmd))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(local)         # before any pinned host buffer is allocated (first touch decides its node)
     dist_ring = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -669,6 +691,7 @@ def main_ours(args):
             "parallelism": (f"batch-sharded x{world}: no data-path collective; one NCCL all-reduce of the step's loss numerators "
                             f"PER STEP on NCCL's side stream, joined only at the end of each {spg}-step graph") if world > 1 else "single GPU",
             "clocks": clocks,
+            "host_affinity": numa,
             "e2e": e2e_obj(wl, e2e_dt, e2e8_dt if wl.kind == "train" else None, h2d, h2d8, d2h, world),
             "gpu_launches": args.steps * wl.launches_per_step(),
             "roofline": roofline_of(wl, ms, kern_us, peak, peak_src, traffic_of(args.workload)),

@@ -892,6 +892,48 @@ def test_warp_perspective_nearest_matches_cv2():
 
 
 
+# ------------------------------------------------------------------------------ robustness of the host layer
+def test_consistency_backward_twice_and_out_of_place():
+    """A second backward through the same node (retain_graph) must give the same gradient again, not None."""
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(2, 4, 36, 64, generator=g).to(DEV).requires_grad_(True)
+    wm = (torch.randint(0, 4, (2, 1, 36, 64), generator=g).float() / 4).to(DEV)
+    loss = sfh_b200.consistency_loss(logits, wm, 4, 0.5)
+    loss.backward(retain_graph=True)
+    g1 = logits.grad.clone()
+    logits.grad = None
+    loss.backward()
+    assert torch.equal(logits.grad, g1) and float(g1.abs().max()) > 0
+    ref = torch.autograd.grad(kr.consistency_loss(logits, wm, 4, 0.5), logits)[0]
+    assert float((g1 - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_stale_template_and_bad_output_buffers_are_not_used():
+    """The fused tails sample a packed copy of court_img: it must be re-staged when court_img is modified in place or
+    swapped.  Caller-supplied output buffers of the wrong layout are replaced, never written through."""
+    W, H, B = 640, 360, 3
+    tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (W, H), 4, 1)
+    img = tmpl.to(DEV).clone()
+    st = mk_stage(img, poi.to(DEV), (W, H), 4, warp_with_nearest=True)
+    th = synth.theta_family_a(B, 2).to(DEV)
+    a = st.predict_tail(th, None, False, False)["warp_mask"].clone()
+    img.mul_(0.0)                                        # in place: the template is now all class 0
+    b = st.predict_tail(th, None, False, False)["warp_mask"]
+    assert int(a.max()) > 0 and int(b.max()) == 0
+    st.court_img = tmpl.to(DEV)                          # swapped back
+    assert torch.equal(st.predict_tail(th, None, False, False)["warp_mask"], a)
+    with pytest.raises(ValueError):                      # a shared template needs identical batch rows
+        bad = tmpl.repeat(2, 1, 1, 1).to(DEV)
+        bad[1] *= 0
+        mk_stage(bad, None, (W, H), 4)
+    # non-contiguous / wrong-dtype `out` buffers
+    big = torch.full((B, H, 2 * W), -7, dtype=torch.int32, device=DEV)
+    out = {"warp_mask": big[:, :, ::2]}                  # right shape, wrong strides
+    r = st.predict_tail(th, None, False, False, out=out)
+    assert torch.equal(r["warp_mask"], a) and r["warp_mask"].is_contiguous() and int(big.min()) == -7 and int(big.max()) == -7
+
+
+
 def test_error_conventions_and_state_dict():
     tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (640, 360), 4, 2)
     st = mk_stage(tmpl.to(DEV), poi.to(DEV), (640, 360), 4)
