@@ -1233,7 +1233,7 @@ static int check_template(const sfh_template* t) {
 }
 
 static void fill_common(FusedParams& p, const float* theta, const sfh_template* t, const float* xs,
-                        const float* ys, int B, int H, int W) {
+                        const float* ys, int B, int H, int W, int ctas_per_sm = SFH_MINCTAS_LIGHT) {
     memset(&p, 0, sizeof(p));
     p.theta = theta; p.xs = xs; p.ys = ys; p.t = *t;
     p.B = B; p.H = H; p.W = W;
@@ -1244,8 +1244,17 @@ static void fill_common(FusedParams& p, const float* theta, const sfh_template* 
     const int tiles_x = (W + kTileW - 1) / kTileW;
     int R = 16;
     if (forced > 0) R = forced;
-    else
-        while (R > 1 && (int64_t)tiles_x * ((H + kWarps * R - 1) / (kWarps * R)) * B < 4 * 3 * 148) R >>= 1;
+    else {
+        auto ctas = [&](int r) { return (int64_t)tiles_x * ((H + kWarps * r - 1) / (kWarps * r)) * B; };
+        while (R > 1 && ctas(R) < 4 * 3 * 148) R >>= 1;
+        // small problems: one full wave of big tiles beats four waves of tiny ones (measured, C1 = 16 frames of
+        // 640x360: R=2 / 1840 CTAs 10.3 us, R=4 8.4 us, R=8 / 480 CTAs 7.9 us, R=16 9.7 us; at R=1 a CTA is all prologue)
+        // (loss / backward epilogues: at most R=8, the tallest tile an int64 gt stage allows, so that int64 and uint8
+        // class ids keep the same tiling and therefore bit-identical sums)
+        const int rmax = ctas_per_sm == SFH_MINCTAS_HEAVY ? 8 : 16;
+        for (int r1 = 2 * R; r1 <= rmax; r1 <<= 1)
+            if (ctas(r1) <= (int64_t)SFH_MINCTAS_LIGHT * 148 && ctas(r1) >= 148) { R = r1; break; }
+    }
     p.rows_per_warp = R;
     p.ntiles = tiles_x * ((H + kWarps * R - 1) / (kWarps * R));
     static const bool no_lean = getenv("SFH_NO_LEAN") != nullptr, no_fast = getenv("SFH_NO_FAST") != nullptr;
@@ -1513,7 +1522,7 @@ int sfh_warp_bwd(const float* theta, const sfh_template* tmpl, const float* xs, 
     if (rc) return rc;
     if (!theta || !grad_out || !dtheta || B <= 0 || H <= 0 || W <= 0) return SFH_E_BADARG;
     FusedParams p;
-    fill_common(p, theta, tmpl, xs, ys, B, H, W);
+    fill_common(p, theta, tmpl, xs, ys, B, H, W, SFH_MINCTAS_HEAVY);
     if ((rc = setup_ws(p, workspace, workspace_bytes))) return rc;
     p.grad_out = grad_out; p.dtheta = dtheta;
     p.vec4 = (W % 4 == 0) && aligned16(grad_out);
@@ -1534,7 +1543,7 @@ int sfh_warp_loss_fwd_bwd(const sfh_template* tmpl, const sfh_train_tail_args* a
     if (a->loss_out && !a->dtheta_total) return SFH_E_BADARG;
     if (a->gt_dtype != SFH_GT_I64 && a->gt_dtype != SFH_GT_U8) return SFH_E_BADARG;
     FusedParams p;
-    fill_common(p, a->theta, tmpl, a->xs, a->ys, a->B, a->H, a->W);
+    fill_common(p, a->theta, tmpl, a->xs, a->ys, a->B, a->H, a->W, SFH_MINCTAS_HEAVY);
     if ((rc = setup_ws(p, a->workspace, a->workspace_bytes))) return rc;
     if (a->gt_dtype == SFH_GT_U8) p.gt8 = (const unsigned char*)a->gt; else p.gt = (const long long*)a->gt;
     p.nc = a->nc; p.kind = a->kind;
