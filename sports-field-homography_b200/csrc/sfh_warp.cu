@@ -315,6 +315,14 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     return v;
 }
 
+// %laneid read again where it is needed: ptxas otherwise keeps `threadIdx.x & 31` alive across the whole patch loop of the
+// 80-register epilogues and spills it (one local-memory reload per band / patch)
+__device__ __forceinline__ int lane_now() {
+    int l;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+    return l;
+}
+
 constexpr int kMaxR = 16;        // bands (8 rows each) per CTA
 constexpr int kPatchW = 16;      // a warp works on 16 x 8 pixel patches: lane = (ly 0..7, lx 0..3), 4 px per lane
 constexpr float kBoxMargin = 1.0f / 64.0f;   // slack (in texels) on the patch bounding box, >> fp32 rounding of ix
@@ -699,30 +707,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
             // packed templates: the geometry and the packed-entry load of pixel j+1 are issued before
             // pixel j's value / loss / chain rule, so one load is always in flight (SFH_PIPE_PIX)
             constexpr bool kPipe = (FMT != SFH_TMPL_F32) && (SFH_PIPE_PIX != 0);
-            Pix qn;
-            unsigned vn = 0u;
-            if (kPipe) {
-                qn = pixel_geom<SMODE>(Hm, __fmul_rn(u[0], Hm.h[0]), __fmul_rn(u[0], Hm.h[3]), __fmul_rn(u[0], Hm.h[6]), v, Wc_f, Hc_f);
-                vn = taps.quad(qn.x0, qn.y0);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                Pix q;
-                TapVals t;
-                if (kPipe) {
-                    q = qn;
-                    const unsigned vq = vn;
-                    if (j < 3) {
-                        qn = pixel_geom<SMODE>(Hm, __fmul_rn(u[j + 1], Hm.h[0]), __fmul_rn(u[j + 1], Hm.h[3]),
-                                               __fmul_rn(u[j + 1], Hm.h[6]), v, Wc_f, Hc_f);
-                        vn = taps.quad(qn.x0, qn.y0);
-                    }
-                    t = taps.decode(vq);
-                } else {
-                    q = pixel_geom<SMODE>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]),
-                                          __fmul_rn(u[j], Hm.h[6]), v, Wc_f, Hc_f);
-                    t = taps.fetch4(0, q.x0, q.y0);
-                }
+            // value, loss and chain rule of one pixel, given its geometry and taps
+            auto finish = [&](int j, const Pix& q, const TapVals& t) {
                 o[j] = bilerp(q, t);
                 const float d = o[j] - tgt[j];
                 float l, g;
@@ -742,6 +728,52 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                     const float giy = ((t.c - t.a) * q.ex + (t.d - t.b) * q.wx) * g;
                     acc.add(q, gix, giy, halfWc, halfHc, u[j]);
                     any = true;
+                }
+            };
+            if (kPipe && lean_patch && p.lean >= 2) {
+                // Guard-free patches: the kernel is bound by the latency of the packed-entry loads (60 % L1 hits, the
+                // rest from L2), not by issue slots.  So the four texel addresses are computed first and all four
+                // loads fly together; the geometry is then evaluated a second time for the weights (24 instructions
+                // per pixel — cheaper than keeping four sets of weights alive in registers at 3 CTAs/SM).
+                unsigned vq4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const Pix q = pixel_geom_lean<SMODE>(Hm, u[j], v, Wc_f, Hc_f);
+                    vq4[j] = taps.quad(q.x0, q.y0);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float uu = u[j];
+                    asm volatile("" : "+f"(uu));             // a fresh value for the compiler: recompute, do not keep
+                    const Pix q = pixel_geom_lean<SMODE>(Hm, uu, v, Wc_f, Hc_f);
+                    finish(j, q, taps.decode(vq4[j]));
+                }
+            } else {
+                Pix qn;
+                unsigned vn = 0u;
+                if (kPipe) {
+                    qn = pixel_geom<SMODE>(Hm, __fmul_rn(u[0], Hm.h[0]), __fmul_rn(u[0], Hm.h[3]), __fmul_rn(u[0], Hm.h[6]), v, Wc_f, Hc_f);
+                    vn = taps.quad(qn.x0, qn.y0);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    Pix q;
+                    TapVals t;
+                    if (kPipe) {
+                        q = qn;
+                        const unsigned vq = vn;
+                        if (j < 3) {
+                            qn = pixel_geom<SMODE>(Hm, __fmul_rn(u[j + 1], Hm.h[0]), __fmul_rn(u[j + 1], Hm.h[3]),
+                                                   __fmul_rn(u[j + 1], Hm.h[6]), v, Wc_f, Hc_f);
+                            vn = taps.quad(qn.x0, qn.y0);
+                        }
+                        t = taps.decode(vq);
+                    } else {
+                        q = pixel_geom<SMODE>(Hm, __fmul_rn(u[j], Hm.h[0]), __fmul_rn(u[j], Hm.h[3]),
+                                              __fmul_rn(u[j], Hm.h[6]), v, Wc_f, Hc_f);
+                        t = taps.fetch4(0, q.x0, q.y0);
+                    }
+                    finish(j, q, t);
                 }
             }
             if (p.out_f) {
@@ -806,35 +838,36 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
     // of ~70: the per-patch bookkeeping is paid once per band.  Placed after the edge-patch loop, where the
     // homography and the chain rule's row sums are dead, so it runs with few live registers.
     if (fast) {
+        const int ln = lane_now();
         const int nbands = nitems >> 3;
         const float inv_nc = p.inv_nc;
         const bool pow2 = p.nc_pow2 != 0;
         const bool hot = EPI == kEpiLoss && tma && !p.gt8 && pow2 && p.out_f != nullptr;
 #pragma unroll 1
         for (int r = warp; r < nbands; r += kWarps) {
-            const int pc = s_cls[r * kWarps + (lane >> 2)];
+            const int pc = s_cls[r * kWarps + (ln >> 2)];
             const bool act = pc >= 0;
             const float cval = taps.class_value(act ? pc : 0);
             const float4 c4 = make_float4(cval, cval, cval, cval);
-            size_t o = base_b + (size_t)(band0 + r * 8) * W + (tx * kTileW + lane * 4);
+            size_t o = base_b + (size_t)(band0 + r * 8) * W + (tx * kTileW + ln * 4);
             if (EPI == kEpiStore) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k, o += W)
                     if (act) __stcs((float4*)(p.out_f + o), c4);
             }
             if (EPI == kEpiLoss) {
-                int so = (r * 8) * kTileW + lane * 4;                    // element offset inside the staged tile
+                int so = (r * 8) * kTileW + ln * 4;                    // element offset inside the staged tile
                 if (hot) {
                     // the reference's own surface (int64 gt staged by TMA, nc a power of two, warp_mask wanted):
                     // 2 LDS.128 + 4 I2F + 4 FFMA + 4 FFMA + 1 STG.128 per row.  fma(g, -1/nc, cval) == cval - g/nc
                     // bit for bit here: g/nc is exact for a power-of-two nc.
-                    // Loads and stores use different lane->pixel maps.  A 128-bit smem load is conflict-free only if
-                    // the 8 lanes of a quarter-warp cover 128 contiguous bytes, so lane i loads gt pixels {2i, 2i+1}
+                    // Loads and stores use different ln->pixel maps.  A 128-bit smem load is conflict-free only if
+                    // the 8 lanes of a quarter-warp cover 128 contiguous bytes, so ln i loads gt pixels {2i, 2i+1}
                     // and {64+2i, 64+2i+1} (patches i/8 and 4+i/8); the store stays one 128-bit line-friendly write of
-                    // pixels 4i..4i+3 (patch i/4).  The loss does not care which lane adds which pixel.
-                    const int pa = s_cls[r * kWarps + (lane >> 3)], pb = s_cls[r * kWarps + 4 + (lane >> 3)];
+                    // pixels 4i..4i+3 (patch i/4).  The loss does not care which ln adds which pixel.
+                    const int pa = s_cls[r * kWarps + (ln >> 3)], pb = s_cls[r * kWarps + 4 + (ln >> 3)];
                     const float ca = taps.class_value(pa >= 0 ? pa : 0), cb = taps.class_value(pb >= 0 ? pb : 0);
-                    const uint32_t sa = smem_u32(s_gt + (r * 8) * kTileW + lane * 2);
+                    const uint32_t sa = smem_u32(s_gt + (r * 8) * kTileW + ln * 2);
                     float* op = p.out_f + o;
                     const float ninv = -inv_nc;
                     float la = 0.f, lb = 0.f;
@@ -893,9 +926,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
                     else __stcs((int4*)(p.out_i + o), make_int4(ci, ci, ci, ci));
                 }
                 if (p.score && p.ratio == 2 && act) {
-                    // the band's 4 x 64 staged logits pixels: lane i owns pixels 2i, 2i+1 of each row; both sit
-                    // under this lane's patch (F.interpolate(nearest) picks source pixel (2i, 2j))
-                    const float* sl = reinterpret_cast<const float*>(s_dyn) + (r * 4) * (kTileW / 2) + lane * 2;
+                    // the band's 4 x 64 staged logits pixels: ln i owns pixels 2i, 2i+1 of each row; both sit
+                    // under this ln's patch (F.interpolate(nearest) picks source pixel (2i, 2j))
+                    const float* sl = reinterpret_cast<const float*>(s_dyn) + (r * 4) * (kTileW / 2) + ln * 2;
                     const int cst = R * 4 * (kTileW / 2);
 #pragma unroll
                     for (int k = 0; k < 4; ++k, sl += kTileW / 2) {
@@ -930,8 +963,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(EPI)) k_fused(const __grid_
         vals[10] = score_sum;
 #pragma unroll
         for (int k = 11; k < 16; ++k) vals[k] = 0.f;
-        const float tot = warp_reduce16(vals, lane);
-        if (!(lane & 1)) s_red[warp][((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = tot;
+        const int ln = lane_now();
+        const float tot = warp_reduce16(vals, ln);
+        if (!(ln & 1)) s_red[threadIdx.x >> 5][((ln >> 4) & 1) * 8 + ((ln >> 3) & 1) * 4 + ((ln >> 2) & 1) * 2 + ((ln >> 1) & 1)] = tot;
     }
     __syncthreads();
     // One partial per (sample, tile, component) in a fixed slot.  In-launch reduction (split_finalize == 0):
@@ -1258,7 +1292,8 @@ static void fill_common(FusedParams& p, const float* theta, const sfh_template* 
     p.rows_per_warp = R;
     p.ntiles = tiles_x * ((H + kWarps * R - 1) / (kWarps * R));
     static const bool no_lean = getenv("SFH_NO_LEAN") != nullptr, no_fast = getenv("SFH_NO_FAST") != nullptr;
-    p.lean = no_lean ? 0 : 1;
+    static const int lean_level = [] { const char* e = getenv("SFH_LEAN_LEVEL"); return e ? atoi(e) : 2; }();
+    p.lean = no_lean ? 0 : lean_level;   // 1: guard-free geometry; 2: + the loss epilogue keeps its four entry loads in flight
     p.fast_free = no_fast ? 0 : 1;
 }
 
