@@ -7,11 +7,13 @@
 //   kEpiLoss    warp + MSE/SmoothL1 vs gt/nc + dL_b/dtheta   train.py:194-197, models/losses.py:35-38
 //   kEpiPredict int32(warp*nc) + CE consistency score        models/reconstructor.py:223-240
 //
-// Layout of one CTA: 8 warps x 32 lanes; a lane owns 4 consecutive output pixels of a row
-// (128-bit stores / 2x128-bit int64 loads, a warp covers 128 px = 512 B of fp32 per row); a warp
-// owns rows {w, w+8} of a 128x16 tile.  The sampling grid lives in registers only.  Per-sample
-// sums (loss, 9 dtheta terms, score) go lane -> warp shuffle -> smem -> one partial per CTA; the
-// last CTA of a sample (ticket counter, no data atomics) adds the partials in fixed order in fp64.
+// Layout of one CTA: 8 warps x 32 lanes on a 128 x 8R pixel tile (R = 1..16 bands of 8 rows) whose gt / logits are
+// staged in smem by one TMA load.  The tile's 16x8 patches are classified against a summed-area table of class edges:
+// patches that touch an edge are processed one per warp (a lane owns 4 consecutive pixels, exact per-pixel geometry,
+// one packed-template load per pixel), the edge-free rest is streamed band by band (a lane owns 32 consecutive bytes
+// of a row).  The sampling grid lives in registers only.  Per-sample sums (loss, 9 dtheta terms, score) go lane -> warp
+// shuffle -> smem -> one partial per CTA, published as tagged 64-bit words; the sample's last-dispatched CTA adds them
+// in fixed order in fp64 inside the same launch (no fences, no data atomics).  See DESIGN.md §4.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
