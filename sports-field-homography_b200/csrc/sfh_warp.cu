@@ -1633,6 +1633,12 @@ int sfh_predict_tail(const sfh_template* tmpl, const sfh_predict_tail_args* a, v
         if ((rc = setup_ws(p, a->workspace, a->workspace_bytes))) return rc;
         p.logits = a->logits; p.lh = a->h; p.lw = a->w; p.score = a->score;
         p.ratio = (a->h == a->H && a->w == a->W) ? 1 : (2 * a->h == a->H && 2 * a->w == a->W) ? 2 : 0;
+        if (p.ratio == 2 && p.rows_per_warp > 8) {
+            // a staged logits tile of 64 x 4R x 4 floats: R = 8 (32 KiB) keeps 4 CTAs per SM resident, R = 16 only 3
+            // (measured on the C5 micro-batch, 256 frames of 1280x720: 391.5 us at R = 16, 378.9 us at R = 8)
+            p.rows_per_warp = 8;
+            p.ntiles = ((a->W + kTileW - 1) / kTileW) * ((a->H + 63) / 64);
+        }
         p.use_tma = make_logits_map(p) ? 1 : 0;
     }
     const bool poi_tail = a->court_poi != nullptr;

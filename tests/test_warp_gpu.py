@@ -775,9 +775,10 @@ def test_c4_full_batch_matches_oracle():
 
 
 def test_c5_micro_batch_matches_oracle():
-    """C5's micro-batch (256 frames of 1280x720, nearest + CE score + POI: R=16 tiles, 64 KB logits TMA box, short
-    bottom tiles remapped to extra z-slices at B=256): a strided sample of 16 frames is compared with the C oracle,
-    the rest through the batch-split property (a frame's result does not depend on its batch)."""
+    """C5's micro-batch (256 frames of 1280x720, nearest + CE score + POI: 3,072 CTAs of 128x64 px with a 32 KB logits
+    TMA box each, short bottom tiles remapped to extra z-slices at B=256, in-launch score reduction over 120 tiles per
+    frame): a strided sample of 16 frames is compared with the C oracle, the rest through the batch-split property (a
+    frame's result does not depend on its batch)."""
     W, H, B = 1280, 720, 256
     tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (W, H), 4, 1)
     th = synth.theta_family_b(B, 55)
