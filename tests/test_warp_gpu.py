@@ -686,7 +686,8 @@ def _guarded(shape, dtype, fill):
     return view, check
 
 
-@pytest.mark.parametrize("W,H,B", [(200, 77, 5), (130, 50, 2), (640, 360, 3), (1276, 716, 2)])
+@pytest.mark.parametrize("W,H,B", [(200, 77, 5), (130, 50, 2), (640, 360, 3), (1276, 716, 2),
+                                   (1280, 720, 2), (128, 8, 40), (256, 72, 20)])      # the last three: full tiles (band streaming)
 def test_no_writes_outside_outputs_at_ragged_sizes(W, H, B):
     tmpl, poi = sfh_b200.load_bundled("ncaa_nc4", (1280, 720) if W > 640 else (640, 360), 4, 1)
     st = mk_stage(tmpl.to(DEV), poi.to(DEV), (W, H), 4, exact=False)
