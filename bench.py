@@ -372,6 +372,11 @@ def time_workload(wl, steps, warmup, use_graph, dist_ring=None, isolated=True):
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
+                    # one eager step on the capture stream first: the library keeps one reduction workspace per
+                    # (device, stream); allocated inside the capture, its zero-fill would be replayed with every graph
+                    one(0, 0)
+                    drain()
+                    side.synchronize()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=side):
                         for j in range(spg):
